@@ -1,0 +1,112 @@
+// Shared definitions for the GBNF B200 kernels: packed-parameter layout, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/gbnf.h"
+
+namespace gbnf {
+
+constexpr int kMaxComponents = 256;   // coef table in shared memory
+constexpr int kMaxD = 256;
+
+// ---- packed parameter layout ---------------------------------------------------------------------------
+// One Linear layer of one coupling net (nn.Linear weight [N_out, K_in], models/layers.py:218-239).
+//   fp32 path : wblob holds Wt[Kp][Np] float (transposed, N contiguous), Kp % 32 == 0, Np % 64 == 0, zero padded.
+//   f16 path  : wblob holds Kp/16 "k-slabs"; slab s is the UMMA canonical K-major no-swizzle image of
+//               W[0:Np, 16s:16s+16]:  [Np/8 row groups][2 k-chunks][8 rows][8 halves]  (SBO = 256 B, LBO = 128 B),
+//               Kp % 16 == 0, Np % 16 == 0, zero padded.  A slab is Np*32 bytes and is what one bulk-TMA moves.
+struct LayerDesc {
+  int K_in, N_out, Kp, Np;
+  long long w_off;   // element offset into wblob (float for fp32, __half for f16)
+  long long b_off;   // float offset into fblob; Np entries, zero padded
+};
+
+// One coupling step of one component.  The kernels never physically permute z: column j of the reference's
+// tensor lives at physical column sigma[j] of the resident row and the composed maps are resolved at pack time
+// (models/layers.py:661-668 Permute1d, models/transformations.py:568-576 flip).
+struct StepDesc {
+  int in_dim, out_dim;   // |z1| (MLP input), |z2| (transformed half)
+  int has_affine;        // ActNorm1d (glow) or eval-mode BatchNorm (realnvp) present
+  int pad_;
+  long long vec_off;     // fblob: add[Dv] | mul[Dv] | off[Dv]  (physical column order), y = (z + add) * mul + off
+  long long idx_off;     // iblob: idx1[in_dim] | idx2[out_dim]  physical columns of z1 / z2
+  LayerDesc layer[2][GBNF_MAX_LAYERS];   // net 0: glow block / realnvp t_net; net 1: realnvp s_net
+};
+
+struct CompDesc {
+  long long sigma_off;   // iblob: final logical->physical map [D]
+  long long const_off;   // fblob: [0] = sum of all data-independent log-det terms, [1] = packed flag
+  long long base_off;    // fblob: mean_phys[Dv] | inv2var_phys[Dv]  (toy base), [2*Dv] = -sum(log s) - D/2 log 2pi
+};
+
+struct ModelDims {
+  int kind, D, Dv, h, K, C, depth, act, coupling, base, nlayers, nnets;
+};
+
+// ---- kernel argument block -----------------------------------------------------------------------------
+struct CouplingArgs {
+  const float* x;
+  long long B;
+  int c0, c1;
+  float* logq;   int ld_logq;      // nullable
+  float* z_out;  float* ldj_out;   // nullable (c1 == c0 + 1)
+  const float* rho; int n_mix; int skip_c; int mix_mode; float* G_ll;   // G_ll nullable
+  const StepDesc* steps;           // [C*K]
+  const CompDesc* comps;           // [C]
+  const float* fblob;
+  const int* iblob;
+  const void* wblob;
+  ModelDims md;
+  int num_tiles;
+  int* error_flag;                 // device int, set non-zero on an internal timeout (f16 path)
+};
+
+// ---- device helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Flat-form mixture coefficients: coef[c] = log r_c + sum_{j>c, j!=skip} log(1 - r_j), r_0 = 1,
+// r_c = rho_c / sum_{j<=c} rho_j (GBNF_MIX_SIMPLEX, density_experiment.py:618) or rho_c (GBNF_MIX_RAW_RHO,
+// models/boosted_flow.py:132-133).  Non-participating components get -inf.  Called by ONE thread.
+__device__ inline void mixture_coefficients(const float* __restrict__ rho, int n, int skip_c, int mix_mode,
+                                            float* coef) {
+  double acc = 0.0;   // sum_{j > c} log(1 - r_j)
+  double pre = 0.0;
+  for (int c = 0; c < n; ++c) pre += (double)rho[c];
+  for (int c = n - 1; c >= 0; --c) {
+    double r = 1.0;
+    if (c > 0) r = (mix_mode == GBNF_MIX_RAW_RHO) ? (double)rho[c] : (double)rho[c] / pre;
+    pre -= (double)rho[c];
+    if (c == skip_c) { coef[c] = -INFINITY; continue; }
+    coef[c] = (float)(log(r) + acc);
+    if (c > 0) acc += log(1.0 - r);
+  }
+}
+
+// Online logsumexp accumulator: (m, s) such that the running value is m + log s.
+struct OnlineLse {
+  float m, s;
+  __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
+  __device__ __forceinline__ void add(float t) {
+    if (t == -INFINITY) return;
+    if (t > m) { s = s * expf(m - t) + 1.f; m = t; }
+    else       { s += expf(t - m); }
+  }
+  __device__ __forceinline__ float value() const { return (s > 0.f) ? m + logf(s) : 0.f; }
+};
+
+}  // namespace gbnf

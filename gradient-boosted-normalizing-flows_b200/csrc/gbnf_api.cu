@@ -1,0 +1,488 @@
+// C-ABI entry points of libgbnf_b200.so (declared in include/gbnf.h).  Host-side planning of the packed layout,
+// workspace management and kernel launches.  No torch types, no exceptions across the boundary.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "pack.cuh"
+#include "mixture.cuh"
+#include "coupling_fp32.cuh"
+#include "coupling_tc.cuh"
+
+using namespace gbnf;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(GBNF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct gbnf_ctx {
+  gbnf_config cfg{};
+  ModelDims md{};
+  int num_sms = 0;
+  std::vector<StepDesc> steps_h;
+  std::vector<CompDesc> comps_h;
+  std::vector<char> packed;
+  StepDesc* steps_d = nullptr;
+  CompDesc* comps_d = nullptr;
+  float* fblob = nullptr;
+  int* iblob = nullptr;
+  void* wblob = nullptr;
+  long long f_count = 0, i_count = 0, w_bytes = 0;
+  const float* base_mean = nullptr;
+  const float* base_scale = nullptr;
+  gbnf_step_params* step_params_d = nullptr;
+  // workspace
+  float* partial = nullptr;      // [max_grid][2]
+  unsigned int* ticket = nullptr;
+  float* ms = nullptr;           // [2]
+  double* wsum = nullptr;        // [1]
+  double* cum = nullptr;         // [cap]
+  double* tile_sums = nullptr;   // [cap_tiles]
+  double* tile_offs = nullptr;   // [cap_tiles + 1]
+  long long cum_cap = 0;
+  int* flags = nullptr;          // [0] kernel error flag, [1] fp16 overflow flag
+  // coupling launch plan
+  int rows_per_cta = 0, ld = 0, out_max = 0, tmem_cols = 0;
+  size_t smem_bytes = 0;
+  TcPlan tc{};
+  int last_grid = 0;
+  long long launches = 0;
+};
+
+namespace {
+
+int plan_layout(gbnf_ctx* h) {
+  const gbnf_config& c = h->cfg;
+  ModelDims& md = h->md;
+  md.kind = c.kind; md.D = c.D; md.Dv = c.D | 1; md.h = c.h; md.K = c.K; md.C = c.C; md.depth = c.depth;
+  md.act = c.act; md.coupling = c.coupling; md.base = c.base;
+  md.nlayers = c.depth + 2;
+  md.nnets = (c.kind == GBNF_KIND_REALNVP) ? 2 : 1;
+  const bool f16 = (c.gemm_mode == GBNF_GEMM_F16_TC);
+  const int kq = f16 ? 16 : kF32KT, nq = f16 ? 16 : kF32NT;
+  const int h0 = c.D / 2, h1 = c.D - h0;
+  long long f = 0, i = 0, w = 0;   // running offsets (floats / ints / weight elements)
+  h->steps_h.assign((size_t)c.C * c.K, StepDesc{});
+  h->comps_h.assign((size_t)c.C, CompDesc{});
+  h->out_max = 0;
+  int kp0_max = 0, np_last_max = 0;
+  for (int cc = 0; cc < c.C; ++cc) {
+    for (int k = 0; k < c.K; ++k) {
+      StepDesc& sd = h->steps_h[(size_t)cc * c.K + k];
+      bool flipped = (c.kind == GBNF_KIND_REALNVP) && (((k + cc) % 2) > 0);
+      sd.in_dim = flipped ? h1 : h0;
+      sd.out_dim = flipped ? h0 : h1;
+      sd.has_affine = 0;   // filled at pack time (device does not read this copy); see pack
+      sd.vec_off = f; f += round_up_ll(3LL * md.Dv, 4);
+      sd.idx_off = i; i += round_up_ll(sd.in_dim + sd.out_dim, 4);
+      h->out_max = std::max(h->out_max, sd.out_dim);
+      int n_last = sd.out_dim;
+      if (c.kind == GBNF_KIND_GLOW && c.coupling == GBNF_COUPLING_AFFINE) n_last = 2 * sd.out_dim;
+      for (int net = 0; net < md.nnets; ++net) {
+        for (int l = 0; l < md.nlayers; ++l) {
+          LayerDesc& L = sd.layer[net][l];
+          L.K_in = (l == 0) ? sd.in_dim : c.h;
+          L.N_out = (l == md.nlayers - 1) ? n_last : c.h;
+          L.Kp = round_up(L.K_in, kq);
+          L.Np = round_up(L.N_out, nq);
+          if (!f16 && l > 0) L.Kp = round_up(c.h, kF32KT);
+          L.w_off = w; w += (long long)L.Kp * L.Np;
+          L.b_off = f; f += round_up_ll(L.Np, 4);
+          if (l == 0) kp0_max = std::max(kp0_max, L.Kp);
+          if (l == md.nlayers - 1) np_last_max = std::max(np_last_max, L.Np);
+        }
+      }
+    }
+    CompDesc& cd = h->comps_h[cc];
+    cd.sigma_off = i; i += round_up_ll(c.D, 4);
+    cd.const_off = f; f += 4;
+    cd.base_off = f; f += round_up_ll(2LL * md.Dv + 1, 4);
+  }
+  h->f_count = f; h->i_count = i;
+  h->w_bytes = w * (f16 ? (long long)sizeof(__half) : (long long)sizeof(float));
+  if (!f16) {
+    const int hp = round_up(c.h, kF32NT);
+    h->rows_per_cta = (hp <= 256) ? 64 : (hp <= 512) ? 32 : 16;
+    h->ld = std::max(hp, std::max(kp0_max, np_last_max)) + 4;
+    size_t fl = (size_t)((h->rows_per_cta * md.Dv + 3) & ~3) + 2ull * h->rows_per_cta * h->ld + 2ull * kF32KT * kF32NT +
+                (size_t)h->rows_per_cta * h->out_max + kMaxComponents + 3ull * h->rows_per_cta;
+    h->smem_bytes = fl * sizeof(float);
+    h->tmem_cols = 0;
+    if (h->smem_bytes > 227 * 1024) return fail(GBNF_ERR_INVALID, "fp32 path: hidden width too large for shared memory");
+  } else {
+    std::string why;
+    if (!tc_make_plan(md, h->steps_h, &h->tc, &why)) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: " + why);
+    h->rows_per_cta = 128;
+    h->smem_bytes = h->tc.smem_bytes;
+    h->tmem_cols = h->tc.tmem_cols;
+  }
+  return GBNF_OK;
+}
+
+int grid_for(const gbnf_ctx* h, long long n_items, int per_block) {
+  long long need = (n_items + per_block - 1) / per_block;
+  long long cap = (long long)h->num_sms * 8;
+  return (int)std::max(1LL, std::min(need, cap));
+}
+
+int ensure_scan_workspace(gbnf_ctx* h, long long B) {
+  if (B <= h->cum_cap) return GBNF_OK;
+  if (h->cum) { cudaFree(h->cum); cudaFree(h->tile_sums); cudaFree(h->tile_offs); h->cum = nullptr; }
+  long long cap = std::max(B, 1LL << 16);
+  long long tiles = (cap + kScanTile - 1) / kScanTile;
+  CUDA_TRY(cudaMalloc(&h->cum, cap * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->tile_sums, tiles * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->tile_offs, (tiles + 1) * sizeof(double)));
+  h->cum_cap = cap;
+  return GBNF_OK;
+}
+
+int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, float* logq, int ld_logq, float* z_out,
+                    float* ldj_out, const float* rho, int n_mix, int skip_c, int mix_mode, float* G_ll, cudaStream_t st) {
+  for (int c = c0; c < c1; ++c)
+    if (!h->packed[c]) return fail(GBNF_ERR_STATE, "component " + std::to_string(c) + " has not been packed");
+  if (B == 0) return GBNF_OK;
+  CouplingArgs a{};
+  a.x = x; a.B = B; a.c0 = c0; a.c1 = c1; a.logq = logq; a.ld_logq = ld_logq; a.z_out = z_out; a.ldj_out = ldj_out;
+  a.rho = rho; a.n_mix = n_mix; a.skip_c = skip_c; a.mix_mode = mix_mode; a.G_ll = G_ll;
+  a.steps = h->steps_d; a.comps = h->comps_d; a.fblob = h->fblob; a.iblob = h->iblob; a.wblob = h->wblob; a.md = h->md;
+  a.error_flag = h->flags;
+  const int R = h->rows_per_cta;
+  a.num_tiles = (int)((B + R - 1) / R);
+  const int grid = std::min(a.num_tiles, h->num_sms);
+  h->last_grid = grid;
+  if (h->cfg.gemm_mode == GBNF_GEMM_FP32) {
+    if (R == 64) coupling_fp32_kernel<64><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
+    else if (R == 32) coupling_fp32_kernel<32><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
+    else coupling_fp32_kernel<16><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
+  } else {
+    int rc = tc_launch(a, h->tc, grid, st);
+    if (rc != 0) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: launch configuration rejected");
+  }
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GBNF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gbnf_abi_version(void) { return GBNF_ABI_VERSION; }
+const char* gbnf_last_error(void) { return g_last_error.c_str(); }
+
+int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
+  if (!out || !cfg) return fail(GBNF_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const gbnf_config& c = *cfg;
+  if (c.kind != GBNF_KIND_REALNVP && c.kind != GBNF_KIND_GLOW) return fail(GBNF_ERR_INVALID, "unknown component kind");
+  if (c.D < 2 || c.D >= kMaxD) return fail(GBNF_ERR_INVALID, "D must be in [2, 255]");
+  if (c.h < 1 || c.K < 1 || c.C < 1 || c.C > kMaxComponents) return fail(GBNF_ERR_INVALID, "bad h / K / C");
+  if (c.depth < 0 || c.depth + 2 > GBNF_MAX_LAYERS) return fail(GBNF_ERR_INVALID, "coupling_network_depth out of range");
+  if (c.act < 0 || c.act > 2 || c.coupling < 0 || c.coupling > 1 || c.base < 0 || c.base > 1)
+    return fail(GBNF_ERR_INVALID, "bad act / coupling / base");
+  if (c.act == GBNF_ACT_MIXED && c.kind != GBNF_KIND_REALNVP) return fail(GBNF_ERR_INVALID, "mixed nets are RealNVP only");
+  if (c.gemm_mode != GBNF_GEMM_FP32 && c.gemm_mode != GBNF_GEMM_F16_TC) return fail(GBNF_ERR_INVALID, "bad gemm_mode");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(GBNF_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (c.device < 0 || c.device >= ndev) return fail(GBNF_ERR_INVALID, "bad device ordinal");
+  CUDA_TRY(cudaSetDevice(c.device));
+  cudaDeviceProp prop{};
+  CUDA_TRY(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major < 10) return fail(GBNF_ERR_CUDA, "device is not sm_100-class (kernels are built for sm_100a only)");
+
+  gbnf_ctx* h = new (std::nothrow) gbnf_ctx();
+  if (!h) return fail(GBNF_ERR_INVALID, "out of host memory");
+  h->cfg = c;
+  h->num_sms = prop.multiProcessorCount;
+  int rc = plan_layout(h);
+  if (rc != GBNF_OK) { delete h; return rc; }
+  h->packed.assign((size_t)c.C, 0);
+#define CREATE_TRY(expr)                                                                                 \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess) { gbnf_destroy(h); return fail(GBNF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } \
+  } while (0)
+  CREATE_TRY(cudaMalloc(&h->steps_d, h->steps_h.size() * sizeof(StepDesc)));
+  CREATE_TRY(cudaMalloc(&h->comps_d, h->comps_h.size() * sizeof(CompDesc)));
+  CREATE_TRY(cudaMalloc(&h->fblob, std::max(1LL, h->f_count) * sizeof(float)));
+  CREATE_TRY(cudaMalloc(&h->iblob, std::max(1LL, h->i_count) * sizeof(int)));
+  CREATE_TRY(cudaMalloc(&h->wblob, std::max(16LL, h->w_bytes)));
+  CREATE_TRY(cudaMemset(h->fblob, 0, std::max(1LL, h->f_count) * sizeof(float)));
+  CREATE_TRY(cudaMalloc(&h->step_params_d, (size_t)c.K * sizeof(gbnf_step_params)));
+  CREATE_TRY(cudaMalloc(&h->partial, (size_t)h->num_sms * 8 * 2 * sizeof(float)));
+  CREATE_TRY(cudaMalloc(&h->ticket, sizeof(unsigned int)));
+  CREATE_TRY(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
+  CREATE_TRY(cudaMalloc(&h->ms, 2 * sizeof(float)));
+  CREATE_TRY(cudaMalloc(&h->wsum, sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->flags, 2 * sizeof(int)));
+  CREATE_TRY(cudaMemset(h->flags, 0, 2 * sizeof(int)));
+  CREATE_TRY(cudaMemcpy(h->comps_d, h->comps_h.data(), h->comps_h.size() * sizeof(CompDesc), cudaMemcpyHostToDevice));
+  if (c.gemm_mode == GBNF_GEMM_FP32) {
+    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  } else {
+    CREATE_TRY(tc_configure(h->tc));
+  }
+#undef CREATE_TRY
+  *out = h;
+  return GBNF_OK;
+}
+
+void gbnf_destroy(gbnf_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->steps_d); cudaFree(h->comps_d); cudaFree(h->fblob); cudaFree(h->iblob); cudaFree(h->wblob);
+  cudaFree(h->step_params_d); cudaFree(h->partial); cudaFree(h->ticket); cudaFree(h->ms); cudaFree(h->wsum);
+  cudaFree(h->cum); cudaFree(h->tile_sums); cudaFree(h->tile_offs); cudaFree(h->flags);
+  delete h;
+}
+
+int gbnf_set_base(gbnf_handle h, const float* d_mean, const float* d_scale, void* stream) {
+  (void)stream;
+  if (!h) return fail(GBNF_ERR_INVALID, "null handle");
+  if (h->cfg.base != GBNF_BASE_DIAG_NORMAL) return fail(GBNF_ERR_INVALID, "handle was not created with GBNF_BASE_DIAG_NORMAL");
+  if (!d_mean || !d_scale) return fail(GBNF_ERR_INVALID, "null base pointers");
+  h->base_mean = d_mean; h->base_scale = d_scale;
+  std::fill(h->packed.begin(), h->packed.end(), 0);   // base constants live in each component's pack
+  return GBNF_OK;
+}
+
+int gbnf_pack_component(gbnf_handle h, int32_t c, const gbnf_component_params* p, void* stream) {
+  if (!h || !p || !p->steps) return fail(GBNF_ERR_INVALID, "null argument");
+  if (c < 0 || c >= h->cfg.C) return fail(GBNF_ERR_INVALID, "component index out of range");
+  if (p->n_steps != h->cfg.K) return fail(GBNF_ERR_INVALID, "n_steps != K");
+  if (h->cfg.kind == GBNF_KIND_REALNVP && p->flip_init != c)
+    return fail(GBNF_ERR_INVALID, "RealNVP component c must have flip_init == c (models/boosted_flow.py:46)");
+  if (h->cfg.base == GBNF_BASE_DIAG_NORMAL && !h->base_mean) return fail(GBNF_ERR_STATE, "call gbnf_set_base first");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const ModelDims& md = h->md;
+  const bool f16 = (h->cfg.gemm_mode == GBNF_GEMM_F16_TC);
+  StepDesc* sd_h = &h->steps_h[(size_t)c * md.K];
+  for (int k = 0; k < md.K; ++k) {
+    const gbnf_step_params& sp = p->steps[k];
+    if (h->cfg.kind == GBNF_KIND_GLOW) {
+      if (!sp.an_bias || !sp.an_logs || !sp.perm) return fail(GBNF_ERR_INVALID, "glow step needs an_bias / an_logs / perm");
+      sd_h[k].has_affine = 1;
+    } else {
+      const int nbn = (sp.bn_log_gamma != nullptr) + (sp.bn_beta != nullptr) + (sp.bn_mean != nullptr) + (sp.bn_var != nullptr);
+      if (nbn != 0 && nbn != 4) return fail(GBNF_ERR_INVALID, "BatchNorm pointers must be all set or all NULL");
+      sd_h[k].has_affine = (nbn == 4);
+    }
+    for (int net = 0; net < md.nnets; ++net)
+      for (int l = 0; l < md.nlayers; ++l)
+        if (!sp.W[net][l] || !sp.b[net][l]) return fail(GBNF_ERR_INVALID, "missing Linear weight / bias pointer");
+  }
+  // stream-ordered pageable copies: the driver stages the host data before returning
+  CUDA_TRY(cudaMemcpyAsync(h->steps_d + (size_t)c * md.K, sd_h, (size_t)md.K * sizeof(StepDesc), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->step_params_d, p->steps, (size_t)md.K * sizeof(gbnf_step_params), cudaMemcpyHostToDevice, st));
+  PackMetaArgs ma{};
+  ma.steps = h->step_params_d; ma.sdesc = h->steps_d + (size_t)c * md.K; ma.cdesc = h->comps_h[c]; ma.md = md;
+  ma.flip_init = p->flip_init; ma.base_mean = h->base_mean; ma.base_scale = h->base_scale; ma.fblob = h->fblob; ma.iblob = h->iblob;
+  pack_meta_kernel<<<1, 32, 0, st>>>(ma);
+  h->launches++;
+  for (int k = 0; k < md.K; ++k) {
+    const gbnf_step_params& sp = p->steps[k];
+    for (int net = 0; net < md.nnets; ++net)
+      for (int l = 0; l < md.nlayers; ++l) {
+        const LayerDesc& L = sd_h[k].layer[net][l];
+        const long long total = (long long)L.Kp * L.Np;
+        const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8);
+        if (f16)
+          pack_weight_f16_kernel<<<grid, 256, 0, st>>>(sp.W[net][l], sp.b[net][l], L, (__half*)h->wblob, h->fblob, h->flags + 1);
+        else
+          pack_weight_fp32_kernel<<<grid, 256, 0, st>>>(sp.W[net][l], sp.b[net][l], L, (float*)h->wblob, h->fblob);
+        h->launches++;
+      }
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (f16) {
+    int ovf = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ovf, h->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (ovf) {
+      CUDA_TRY(cudaMemsetAsync(h->flags + 1, 0, sizeof(int), st));
+      return fail(GBNF_ERR_NUMERIC, "a weight is not finite in fp16; use GBNF_GEMM_FP32 for this model");
+    }
+  }
+  h->packed[c] = 1;
+  return GBNF_OK;
+}
+
+int gbnf_component_logq(gbnf_handle h, const float* d_x, int64_t B, int32_t c0, int32_t c1, float* d_logq,
+                        float* d_z_opt, float* d_ldj_opt, void* stream) {
+  if (!h) return fail(GBNF_ERR_INVALID, "null handle");
+  if (B < 0 || c0 < 0 || c1 > h->cfg.C || c0 >= c1) return fail(GBNF_ERR_INVALID, "bad B or component range");
+  if ((d_z_opt || d_ldj_opt) && c1 != c0 + 1) return fail(GBNF_ERR_INVALID, "z / ldj outputs need a single component");
+  if (B > 0 && !d_x) return fail(GBNF_ERR_INVALID, "null x");
+  if (!d_logq && !d_z_opt && !d_ldj_opt) return fail(GBNF_ERR_INVALID, "no output requested");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  return launch_coupling(h, d_x, B, c0, c1, d_logq, c1 - c0, d_z_opt, d_ldj_opt, nullptr, 0, -1, 0, nullptr,
+                         (cudaStream_t)stream);
+}
+
+int gbnf_mixture_logdensity(gbnf_handle h, const float* d_logq, int64_t B, int32_t ld, int32_t n_comp,
+                            const float* d_rho, int32_t skip_c, int32_t mix_mode, float* d_G_ll, void* stream) {
+  if (!h) return fail(GBNF_ERR_INVALID, "null handle");
+  if (B < 0 || n_comp < 0 || n_comp > kMaxComponents || ld < n_comp) return fail(GBNF_ERR_INVALID, "bad B / n_comp / ld");
+  if (skip_c == 0) return fail(GBNF_ERR_INVALID, "skip_c == 0 is not reachable in the reference (toy_experiment.py:409)");
+  if (B == 0) return GBNF_OK;
+  if (!d_G_ll || (n_comp > 0 && (!d_logq || !d_rho))) return fail(GBNF_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  mixture_lse_kernel<<<grid_for(h, B, kMixThreads), kMixThreads, 0, (cudaStream_t)stream>>>(d_logq, B, ld, n_comp, d_rho,
+                                                                                         skip_c, mix_mode, d_G_ll);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GBNF_OK;
+}
+
+int gbnf_fused_eval(gbnf_handle h, const float* d_x, int64_t B, int32_t n_comp, const float* d_rho, int32_t skip_c,
+                    int32_t mix_mode, float* d_G_ll, float* d_logq_opt, void* stream) {
+  if (!h) return fail(GBNF_ERR_INVALID, "null handle");
+  if (B < 0 || n_comp < 0 || n_comp > h->cfg.C) return fail(GBNF_ERR_INVALID, "bad B / n_comp");
+  if (skip_c == 0) return fail(GBNF_ERR_INVALID, "skip_c == 0 is not reachable in the reference (toy_experiment.py:409)");
+  if (B == 0) return GBNF_OK;
+  if (!d_G_ll) return fail(GBNF_ERR_INVALID, "null G_ll");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (n_comp == 0) {   // G_ll = zeros, density_experiment.py:612
+    CUDA_TRY(cudaMemsetAsync(d_G_ll, 0, (size_t)B * sizeof(float), (cudaStream_t)stream));
+    return GBNF_OK;
+  }
+  if (!d_x || !d_rho) return fail(GBNF_ERR_INVALID, "null pointer");
+  return launch_coupling(h, d_x, B, 0, n_comp, d_logq_opt, n_comp, nullptr, nullptr, d_rho, n_comp, skip_c, mix_mode, d_G_ll,
+                         (cudaStream_t)stream);
+}
+
+int gbnf_weight_stats(gbnf_handle h, const float* d_G_ll, int64_t B, float* d_ms, void* stream) {
+  if (!h || !d_G_ll || !d_ms || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  softmax_stats_kernel<<<grid_for(h, B, kMixThreads * 4), kMixThreads, 0, (cudaStream_t)stream>>>(d_G_ll, B, h->partial,
+                                                                                              h->ticket, d_ms);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GBNF_OK;
+}
+
+int gbnf_weight_apply(gbnf_handle h, const float* d_G_ll, int64_t B, const float* d_ms, float clamp_lo, float clamp_hi,
+                      int32_t mode, float* d_w, double* d_wsum, void* stream) {
+  (void)mode;
+  if (!h || !d_G_ll || !d_ms || !d_w || !d_wsum || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  zero_double_kernel<<<1, 1, 0, st>>>(d_wsum);
+  weight_apply_kernel<<<grid_for(h, B, kMixThreads * 4), kMixThreads, 0, st>>>(d_G_ll, B, d_ms, clamp_lo, clamp_hi, d_w,
+                                                                             d_wsum, nullptr);
+  h->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return GBNF_OK;
+}
+
+int gbnf_weight_renorm(gbnf_handle h, float* d_w, int64_t B, const double* d_wsum, int32_t mode, void* stream) {
+  if (!h || !d_w || !d_wsum || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  weight_renorm_kernel<<<grid_for(h, B, kMixThreads * 4), kMixThreads, 0, (cudaStream_t)stream>>>(
+      d_w, B, d_wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, nullptr);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GBNF_OK;
+}
+
+int gbnf_boost_weights(gbnf_handle h, const float* d_G_ll, int64_t B, float clamp_lo, float clamp_hi, int32_t mode,
+                       float* d_w, float* d_stats, void* stream) {
+  if (!h || !d_G_ll || !d_w || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
+  if (mode != GBNF_WEIGHTS_DENSITY && mode != GBNF_WEIGHTS_TOY) return fail(GBNF_ERR_INVALID, "bad weights mode");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(h, B, kMixThreads * 4);
+  softmax_stats_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->partial, h->ticket, h->ms);
+  zero_double_kernel<<<1, 1, 0, st>>>(h->wsum);
+  weight_apply_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->ms, clamp_lo, clamp_hi, d_w, h->wsum, d_stats);
+  weight_renorm_kernel<<<g, kMixThreads, 0, st>>>(d_w, B, h->wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, d_stats);
+  h->launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  return GBNF_OK;
+}
+
+int gbnf_resample(gbnf_handle h, const float* d_w, int64_t B, const double* d_u, int64_t n, int64_t* d_idx, void* stream) {
+  if (!h || !d_w || B <= 0 || n < 0) return fail(GBNF_ERR_INVALID, "bad argument");
+  if (n == 0) return GBNF_OK;
+  if (!d_u || !d_idx) return fail(GBNF_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = ensure_scan_workspace(h, B);
+  if (rc != GBNF_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles = (int)((B + kScanTile - 1) / kScanTile);
+  scan_tile_sums_kernel<<<tiles, kScanThreads, 0, st>>>(d_w, B, h->tile_sums);
+  scan_tile_offsets_kernel<<<1, kScanThreads, 0, st>>>(h->tile_sums, tiles, h->tile_offs);
+  scan_finalize_kernel<<<tiles, kScanThreads, 0, st>>>(d_w, B, h->tile_offs, tiles, h->cum);
+  resample_search_kernel<<<grid_for(h, n, kMixThreads), kMixThreads, 0, st>>>(h->cum, B, d_u, n, (long long*)d_idx);
+  h->launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  return GBNF_OK;
+}
+
+int gbnf_gather_rows(gbnf_handle h, const float* d_x, int32_t D, const int64_t* d_idx, int64_t n, float* d_out, void* stream) {
+  if (!h || D <= 0 || n < 0) return fail(GBNF_ERR_INVALID, "bad argument");
+  if (n == 0) return GBNF_OK;
+  if (!d_x || !d_idx || !d_out) return fail(GBNF_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  gather_rows_kernel<<<grid_for(h, n * 32, kMixThreads), kMixThreads, 0, (cudaStream_t)stream>>>(
+      d_x, D, (const long long*)d_idx, n, d_out);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GBNF_OK;
+}
+
+int gbnf_sample_component(const float* rho_host, int32_t n, double u, int32_t exclude, int32_t* j_out) {
+  if (!rho_host || !j_out || n <= 0 || exclude >= n) return fail(GBNF_ERR_INVALID, "bad argument");
+  double total = 0.0;
+  for (int i = 0; i < n; ++i) if (i != exclude) total += (double)rho_host[i];
+  if (!(total > 0.0)) return fail(GBNF_ERR_INVALID, "rho has no mass");
+  double run = 0.0;
+  int j = 0;
+  for (int i = 0; i < n; ++i) {
+    run += (i == exclude) ? 0.0 : (double)rho_host[i];
+    if (run / total < u) j = i + 1; else break;
+  }
+  *j_out = std::min(j, n - 1);
+  return GBNF_OK;
+}
+
+int gbnf_get_info(gbnf_handle h, gbnf_info* out) {
+  if (!h || !out) return fail(GBNF_ERR_INVALID, "null argument");
+  out->gemm_mode = h->cfg.gemm_mode;
+  out->rows_per_cta = h->rows_per_cta;
+  out->smem_bytes = (int32_t)h->smem_bytes;
+  out->tmem_cols = h->tmem_cols;
+  out->num_sms = h->num_sms;
+  out->grid = h->last_grid;
+  out->packed_bytes = h->w_bytes + h->f_count * 4 + h->i_count * 4;
+  out->launches = h->launches;
+  return GBNF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+// Mixture logsumexp, boosting weights, inverse-CDF resampling, row gather.  All HBM-bound streaming kernels:
+// 128-bit loads where the row length allows it, warp-shuffle reductions, grids sized in multiples of the SM count.
+#pragma once
+#include "common.cuh"
+
+namespace gbnf {
+
+constexpr int kMixThreads = 256;
+
+// ---- G_ll[b] = logsumexp_c(coef[c] + logq[b, c]) ---------------------------------------------------------
+// One thread per row; a warp reads 32 consecutive rows = one contiguous span of 32*ld floats.  With ld % 4 == 0
+// the row is fetched with 128-bit loads.
+__global__ void __launch_bounds__(kMixThreads) mixture_lse_kernel(const float* __restrict__ logq, long long B, int ld,
+                                                                 int n, const float* __restrict__ rho, int skip_c,
+                                                                 int mix_mode, float* __restrict__ G_ll) {
+  __shared__ float coef[kMaxComponents];
+  if (threadIdx.x == 0) mixture_coefficients(rho, n, skip_c, mix_mode, coef);
+  __syncthreads();
+  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logq) & 15) == 0);
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    const float* row = logq + b * ld;
+    OnlineLse o; o.init();
+    int c = 0;
+    if (vec) {
+      for (; c + 4 <= n; c += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
+        o.add(coef[c] + v.x); o.add(coef[c + 1] + v.y); o.add(coef[c + 2] + v.z); o.add(coef[c + 3] + v.w);
+      }
+    }
+    for (; c < n; ++c) o.add(coef[c] + __ldg(row + c));
+    G_ll[b] = o.value();
+  }
+}
+
+// ---- batch softmax statistics of u = -G_ll: (max, sum exp(u - max)) ----------------------------------------
+// Block partials -> the last block to finish folds them (threadfence + atomic ticket), so one launch suffices.
+struct MsPair { float m, s; };
+__device__ __forceinline__ MsPair ms_merge(MsPair a, MsPair b) {
+  if (b.m == -INFINITY) return a;
+  if (a.m == -INFINITY) return b;
+  MsPair r;
+  r.m = fmaxf(a.m, b.m);
+  r.s = a.s * expf(a.m - r.m) + b.s * expf(b.m - r.m);
+  return r;
+}
+__device__ __forceinline__ MsPair ms_warp_reduce(MsPair v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MsPair w;
+    w.m = __shfl_xor_sync(0xffffffffu, v.m, o);
+    w.s = __shfl_xor_sync(0xffffffffu, v.s, o);
+    v = ms_merge(v, w);
+  }
+  return v;
+}
+__device__ inline MsPair ms_block_reduce(MsPair v, MsPair* sm /* [32] */) {
+  v = ms_warp_reduce(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  MsPair r; r.m = -INFINITY; r.s = 0.f;
+  if (wid == 0) {
+    if (lane < (int)(blockDim.x >> 5)) r = sm[lane];
+    r = ms_warp_reduce(r);
+  }
+  __syncthreads();
+  return r;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(kMixThreads) softmax_stats_kernel(const float* __restrict__ G_ll, long long B,
+                                                                   float* __restrict__ partial /* [grid][2] */,
+                                                                   unsigned int* __restrict__ ticket,
+                                                                   float* __restrict__ ms_out /* [2] */) {
+  __shared__ MsPair sm[32];
+  __shared__ bool is_last;
+  // pass 1 (thread-local): two-sweep max / sum over a strided slice keeps exp() calls to one per element
+  MsPair v; v.m = -INFINITY; v.s = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long i = i0; i < B; i += stride) v.m = fmaxf(v.m, -__ldg(G_ll + i));
+  for (long long i = i0; i < B; i += stride) v.s += expf(-__ldg(G_ll + i) - v.m);
+  MsPair r = ms_block_reduce(v, sm);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = r.m;
+    partial[2 * blockIdx.x + 1] = r.s;
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    MsPair w; w.m = -INFINITY; w.s = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+      MsPair p; p.m = __ldcg(partial + 2 * i); p.s = __ldcg(partial + 2 * i + 1);
+      w = ms_merge(w, p);
+    }
+    MsPair f = ms_block_reduce(w, sm);
+    if (threadIdx.x == 0) { ms_out[0] = f.m; ms_out[1] = f.s; *ticket = 0u; }
+  }
+}
+
+// ---- weights from (max, sum): w = exp(u - max) / sum, optional clamp; accumulates sum(w) in fp64 -------------
+// density (density_experiment.py:638-641): clamp to [lo, hi] iff max w > hi, and max w == fl(1 / sum) because the
+// largest exp() term is exactly 1.  toy (toy_experiment.py:440,453-459): w is first renormalised by its own sum
+// (== 1 up to rounding; the kernel folds that first division into `inv_first`), clamp iff max > hi.
+__global__ void __launch_bounds__(kMixThreads) weight_apply_kernel(const float* __restrict__ G_ll, long long B,
+                                                                  const float* __restrict__ ms, float lo, float hi,
+                                                                  float* __restrict__ w, double* __restrict__ wsum,
+                                                                  float* __restrict__ stats_opt) {
+  __shared__ double sm[32];
+  const float M = ms[0], S = ms[1];
+  const float wmax = 1.0f / S;
+  const bool clamp = wmax > hi;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+    float v = expf(-__ldg(G_ll + i) - M) / S;
+    if (clamp) v = fmaxf(fminf(v, hi), lo);
+    w[i] = v;
+    acc += (double)v;
+  }
+  acc = warp_sum(acc);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    double t = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) atomicAdd(wsum, t);
+  }
+  if (stats_opt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    stats_opt[0] = M; stats_opt[1] = S; stats_opt[2] = clamp ? 1.f : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kMixThreads) weight_renorm_kernel(float* __restrict__ w, long long B,
+                                                                   const double* __restrict__ wsum, int always,
+                                                                   float* __restrict__ stats_opt) {
+  const float s = (float)(*wsum);
+  if (stats_opt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) stats_opt[3] = s;
+  if (!always && s == 1.0f) return;            // `if weights.sum() != 1.0` density_experiment.py:640 (toy: always)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x)
+    w[i] = w[i] / s;
+}
+
+__global__ void zero_double_kernel(double* p) { *p = 0.0; }
+
+// ---- inverse-CDF resampling: fp64 inclusive scan of w, then left binary search per uniform ---------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;                      // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ inline double block_exclusive_scan(double v, double* sm /* [32] */, double* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) sm[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    double s = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0.0;
+    double si = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) si += t;
+    }
+    sm[lane] = si - s;                              // exclusive warp offsets
+    if (lane == 31) *total = si;
+  }
+  __syncthreads();
+  const double r = sm[wid] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+// pass 1: per-tile sums
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const float* __restrict__ w, long long B,
+                                                                     double* __restrict__ tile_sums) {
+  __shared__ double sm[32];
+  const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) if (base + i < B) s += (double)w[base + i];   // sequential within a thread
+  s = warp_sum(s);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    double t = (lane < kScanThreads / 32) ? sm[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) tile_sums[blockIdx.x] = t;
+  }
+}
+// pass 2: exclusive scan of tile sums (single block, sequential chunks), total at tile_offs[num_tiles]
+__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(const double* __restrict__ tile_sums,
+                                                                        int num_tiles, double* __restrict__ tile_offs) {
+  __shared__ double sm[32];
+  __shared__ double total;
+  double carry = 0.0;
+  for (int base = 0; base < num_tiles; base += kScanThreads) {
+    const int i = base + threadIdx.x;
+    const double v = (i < num_tiles) ? tile_sums[i] : 0.0;
+    const double ex = block_exclusive_scan(v, sm, &total);
+    if (i < num_tiles) tile_offs[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_offs[num_tiles] = carry;
+}
+// pass 3: cum[i] = (offset + inclusive prefix) / total
+__global__ void __launch_bounds__(kScanThreads) scan_finalize_kernel(const float* __restrict__ w, long long B,
+                                                                    const double* __restrict__ tile_offs, int num_tiles,
+                                                                    double* __restrict__ cum) {
+  __shared__ double sm[32];
+  __shared__ double total_tile;
+  const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  double v[kScanItems];
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { v[i] = (base + i < B) ? (double)w[base + i] : 0.0; s += v[i]; }
+  double run = tile_offs[blockIdx.x] + block_exclusive_scan(s, sm, &total_tile);
+  const double total = tile_offs[num_tiles];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    run += v[i];
+    if (base + i < B) cum[base + i] = run / total;
+  }
+}
+// idx[i] = #{k : cum_k < u_i}  (searchsorted side='left'), clamped to B-1
+__global__ void __launch_bounds__(kMixThreads) resample_search_kernel(const double* __restrict__ cum, long long B,
+                                                                     const double* __restrict__ u, long long n,
+                                                                     long long* __restrict__ idx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double ui = u[i];
+    long long lo = 0, hi = B;
+    while (lo < hi) {
+      const long long mid = lo + ((hi - lo) >> 1);
+      if (__ldg(cum + mid) < ui) lo = mid + 1; else hi = mid;
+    }
+    idx[i] = lo < B - 1 ? lo : B - 1;
+  }
+}
+
+// out[i, :] = x[idx[i], :]   (density_experiment.py:644).  One warp per row, lanes stride the row.
+__global__ void __launch_bounds__(kMixThreads) gather_rows_kernel(const float* __restrict__ x, int D,
+                                                                 const long long* __restrict__ idx, long long n,
+                                                                 float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = warp; i < n; i += nwarps) {
+    const float* src = x + idx[i] * (long long)D;
+    float* dst = out + i * (long long)D;
+    for (int j = lane; j < D; j += 32) dst[j] = __ldg(src + j);
+  }
+}
+
+}  // namespace gbnf

@@ -1,0 +1,128 @@
+// Parameter re-tiling: raw reference tensors (device) -> the handle's packed blobs (device).
+#pragma once
+#include "common.cuh"
+
+namespace gbnf {
+
+// Device copy of gbnf_step_params plus what the meta kernel needs.
+struct PackMetaArgs {
+  const gbnf_step_params* steps;   // device array [K]
+  const StepDesc* sdesc;           // device array [K] (this component's slice)
+  CompDesc cdesc;
+  ModelDims md;
+  int flip_init;
+  const float* base_mean;          // logical order, may be null
+  const float* base_scale;
+  float* fblob;
+  int* iblob;
+};
+
+// Composes the permutations / flips of one component and writes, per step, the elementwise affine constants in
+// physical column order, the gather indices of z1 / z2, and the component's data-independent log-det constant.
+//   Glow   : ActNorm1d (models/layers.py:488-518) then Permute1d (models/layers.py:661-668) then split (utilities.py:153).
+//   RealNVP: eval-mode BatchNorm (models/layers.py:349-358) then flip/split (models/transformations.py:568-576).
+// Tiny and sequential by nature (K * D elements): one thread.
+__global__ void pack_meta_kernel(PackMetaArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int D = a.md.D, Dv = a.md.Dv, h0 = D / 2, h1 = D - h0;
+  int sigma[kMaxD], tmp[kMaxD];
+  for (int j = 0; j < D; ++j) sigma[j] = j;
+  double ldj_const = 0.0;
+  for (int k = 0; k < a.md.K; ++k) {
+    const gbnf_step_params& sp = a.steps[k];
+    const StepDesc& sd = a.sdesc[k];
+    float* add = a.fblob + sd.vec_off;
+    float* mul = add + Dv;
+    float* off = mul + Dv;
+    int* idx1 = a.iblob + sd.idx_off;
+    int* idx2 = idx1 + sd.in_dim;
+    for (int p = 0; p < Dv; ++p) { add[p] = 0.f; mul[p] = 1.f; off[p] = 0.f; }
+    if (a.md.kind == GBNF_KIND_GLOW) {
+      for (int j = 0; j < D; ++j) {
+        add[sigma[j]] = sp.an_bias[j];
+        mul[sigma[j]] = expf(sp.an_logs[j]);
+        ldj_const += (double)sp.an_logs[j];
+      }
+      for (int j = 0; j < D; ++j) tmp[j] = sigma[(int)sp.perm[j]];
+      for (int j = 0; j < D; ++j) sigma[j] = tmp[j];
+      for (int j = 0; j < h0; ++j) idx1[j] = sigma[j];
+      for (int j = 0; j < h1; ++j) idx2[j] = sigma[h0 + j];
+    } else {
+      if (sp.bn_mean != nullptr) {
+        for (int j = 0; j < D; ++j) {
+          double var = (double)sp.bn_var[j] + 1e-5;
+          add[sigma[j]] = -sp.bn_mean[j];
+          mul[sigma[j]] = (float)(exp((double)sp.bn_log_gamma[j]) / sqrt(var));
+          off[sigma[j]] = sp.bn_beta[j];
+          ldj_const += (double)sp.bn_log_gamma[j] - 0.5 * log(var);
+        }
+      }
+      const bool flipped = ((k + a.flip_init) % 2) > 0;
+      if (!flipped) {
+        for (int j = 0; j < h0; ++j) idx1[j] = sigma[j];
+        for (int j = 0; j < h1; ++j) idx2[j] = sigma[h0 + j];
+      } else {
+        for (int j = 0; j < h1; ++j) idx1[j] = sigma[h0 + j];
+        for (int j = 0; j < h0; ++j) idx2[j] = sigma[j];
+        for (int j = 0; j < h1; ++j) tmp[j] = sigma[h0 + j];      // output is [z1, z2'] for both flips
+        for (int j = 0; j < h0; ++j) tmp[h1 + j] = sigma[j];
+        for (int j = 0; j < D; ++j) sigma[j] = tmp[j];
+      }
+    }
+  }
+  int* sig_out = a.iblob + a.cdesc.sigma_off;
+  for (int j = 0; j < D; ++j) sig_out[j] = sigma[j];
+  a.fblob[a.cdesc.const_off] = (float)ldj_const;
+  a.fblob[a.cdesc.const_off + 1] = 1.f;
+  // base density constants in physical order
+  float* bm = a.fblob + a.cdesc.base_off;
+  float* bi = bm + Dv;
+  double c0 = -0.5 * (double)D * 1.8378770664093453;   // -D/2 log(2 pi)
+  for (int p = 0; p < Dv; ++p) { bm[p] = 0.f; bi[p] = 0.f; }
+  if (a.md.base == GBNF_BASE_DIAG_NORMAL && a.base_mean != nullptr) {
+    for (int j = 0; j < D; ++j) {
+      double s = (double)a.base_scale[j];
+      bm[sigma[j]] = a.base_mean[j];
+      bi[sigma[j]] = (float)(1.0 / (2.0 * s * s));
+      c0 -= log(s);
+    }
+  } else {
+    for (int j = 0; j < D; ++j) bi[sigma[j]] = 0.5f;
+  }
+  bm[2 * Dv] = (float)c0;
+}
+
+// fp32 path: dst[k][n] = W[n][k] (zero padded).
+__global__ void pack_weight_fp32_kernel(const float* __restrict__ W, const float* __restrict__ b, LayerDesc ld,
+                                        float* __restrict__ wblob, float* __restrict__ fblob) {
+  const long long total = (long long)ld.Kp * ld.Np;
+  float* dst = wblob + ld.w_off;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i / ld.Np), n = (int)(i % ld.Np);
+    dst[i] = (k < ld.K_in && n < ld.N_out) ? W[(long long)n * ld.K_in + k] : 0.f;
+  }
+  if (blockIdx.x == 0)
+    for (int n = threadIdx.x; n < ld.Np; n += blockDim.x) fblob[ld.b_off + n] = (n < ld.N_out) ? b[n] : 0.f;
+}
+
+// f16 path: UMMA canonical K-major no-swizzle k-slabs (see LayerDesc).  Sets *overflow if |w| is not finite in fp16.
+__global__ void pack_weight_f16_kernel(const float* __restrict__ W, const float* __restrict__ b, LayerDesc ld,
+                                       __half* __restrict__ wblob, float* __restrict__ fblob, int* overflow) {
+  const long long total = (long long)ld.Kp * ld.Np;
+  __half* dst = wblob + ld.w_off;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // decode destination index -> (n, k)
+    long long slab = i / ((long long)ld.Np * 16);
+    int r = (int)(i % ((long long)ld.Np * 16));
+    int grp = r / 128, kc = (r % 128) / 64, row = (r % 64) / 8, e = r % 8;
+    int n = grp * 8 + row, k = (int)slab * 16 + kc * 8 + e;
+    float v = (k < ld.K_in && n < ld.N_out) ? W[(long long)n * ld.K_in + k] : 0.f;
+    __half hv = __float2half_rn(v);
+    if (__hisinf(hv) || __hisnan(hv)) *overflow = 1;
+    dst[i] = hv;
+  }
+  if (blockIdx.x == 0)
+    for (int n = threadIdx.x; n < ld.Np; n += blockDim.x) fblob[ld.b_off + n] = (n < ld.N_out) ? b[n] : 0.f;
+}
+
+}  // namespace gbnf

@@ -1,0 +1,40 @@
+"""BoostedFlow module tree -> plain "model dict" of numpy arrays (the container the CPU oracle and the golden
+fixtures use; format documented in oracle/gbnf_oracle.py).  Works on this package's modules AND on the reference's
+(same attribute layout), which is how tests/golden/make_golden.py feeds reference models to the oracle."""
+import numpy as np
+import torch
+
+
+def _np(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def _linears(net):
+    return [(_np(m.weight), _np(m.bias)) for m in net.network if isinstance(m, torch.nn.Linear)]
+
+
+def extract_model(model, toy_base=False):
+    args = model.args
+    kind = args.component_type
+    md = {"kind": kind, "D": int(args.z_size), "h": int(args.h_size), "K": int(args.num_flows),
+          "C": int(args.num_components), "depth": int(args.coupling_network_depth),
+          "act": args.coupling_network, "coupling": getattr(args, "flow_coupling", "affine") if kind == "glow" else "affine",
+          "rho": _np(model.rho).astype(np.float32), "base_mean": None, "base_scale": None, "components": []}
+    if toy_base:
+        md["base_mean"], md["base_scale"] = _np(model.base_dist_mean), _np(model.base_dist_var)
+    for c, flow in enumerate(model.flows):
+        steps = []
+        if kind == "glow":
+            for st in flow.flow.layers:
+                perm = st.shuffle if hasattr(st, "shuffle") else st.reverse
+                steps.append({"an_bias": _np(st.actnorm.bias).reshape(-1), "an_logs": _np(st.actnorm.logs).reshape(-1),
+                              "perm": _np(perm.indices).astype(np.int64), "net": _linears(st.block)})
+        else:
+            for (t_net, s_net, bn) in flow.flow_param:
+                b = None
+                if bn is not None:
+                    b = {"log_gamma": _np(bn.log_gamma), "beta": _np(bn.beta), "mean": _np(bn.running_mean),
+                         "var": _np(bn.running_var)}
+                steps.append({"bn": b, "t": _linears(t_net), "s": _linears(s_net)})
+        md["components"].append({"flip_init": int(getattr(flow, "flip_init", 0)), "steps": steps})
+    return md

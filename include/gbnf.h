@@ -1,0 +1,177 @@
+/*
+ * gbnf.h -- C ABI of the B200-native boosted-mixture density path (libgbnf_b200.so).
+ *
+ * Scope: the ONE hot path of robert-giaquinto/gradient-boosted-normalizing-flows named in BASELINE.json:
+ * per-component log q_c(x) for C fixed RealNVP / Glow coupling stacks, the rho-weighted logsumexp mixture,
+ * the boosting weights, inverse-CDF resampling.  The reference has no FFI (it is pure PyTorch); each entry
+ * point below cites the reference Python it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* / documented "device" is a CUDA device pointer that the
+ *     caller owns (PyTorch tensors in practice) and that is only BORROWED for the duration of the call;
+ *   - all tensors are contiguous row-major, float32 unless stated; indices are int64;
+ *   - every launch goes on the caller's stream (`stream` is a cudaStream_t passed as void*); no entry point
+ *     synchronises the device unless documented;
+ *   - every entry returns 0 on success or a negative gbnf_status; gbnf_last_error() gives the text
+ *     (thread-local); no C++ exception crosses the boundary;
+ *   - one handle per device; calls on one handle are not re-entrant;
+ *   - there is NO CPU fallback: without a CUDA device gbnf_create fails with GBNF_ERR_CUDA.
+ */
+#ifndef GBNF_H_
+#define GBNF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBNF_ABI_VERSION 1
+#define GBNF_MAX_LAYERS 6 /* depth + 2 <= 6 */
+
+typedef struct gbnf_ctx* gbnf_handle;
+
+typedef enum {
+  GBNF_OK = 0,
+  GBNF_ERR_INVALID = -1, /* bad argument / unsupported configuration */
+  GBNF_ERR_CUDA = -2,    /* CUDA runtime error (text in gbnf_last_error) */
+  GBNF_ERR_STATE = -3,   /* e.g. component not packed yet */
+  GBNF_ERR_NUMERIC = -4  /* weights not representable in the selected GEMM operand type */
+} gbnf_status;
+
+enum { GBNF_KIND_REALNVP = 0, GBNF_KIND_GLOW = 1 };              /* models/boosted_flow.py:44-50 */
+enum { GBNF_ACT_TANH = 0, GBNF_ACT_RELU = 1, GBNF_ACT_MIXED = 2 }; /* models/realnvp.py:47-66 (mixed: t=ReLU, s=Tanh) */
+enum { GBNF_COUPLING_AFFINE = 0, GBNF_COUPLING_ADDITIVE = 1 };     /* models/glow.py:326-338 */
+enum { GBNF_BASE_STD_NORMAL = 0, GBNF_BASE_DIAG_NORMAL = 1 };     /* utils/distributions.py:44 | generative_flow.py:38-42 */
+enum {
+  GBNF_GEMM_FP32 = 0,  /* CUDA-core fp32 FMA, libm-accurate tanh: reference-class numerics (~1e-6 rel)          */
+  GBNF_GEMM_F16_TC = 1 /* tcgen05 tensor cores, fp16 operands, fp32 accumulate in TMEM (<=1e-4 rel on log q)    */
+};
+enum { GBNF_WEIGHTS_DENSITY = 0, GBNF_WEIGHTS_TOY = 1 }; /* density_experiment.py:627-641 | toy_experiment.py:440-459 */
+enum { GBNF_MIX_SIMPLEX = 0, GBNF_MIX_RAW_RHO = 1 };     /* density_experiment.py:618 | models/boosted_flow.py:132-133 */
+
+typedef struct {
+  int32_t kind;      /* GBNF_KIND_* */
+  int32_t D;         /* features (args.z_size) */
+  int32_t h;         /* hidden width (args.h_size) */
+  int32_t K;         /* coupling steps per component (args.num_flows) */
+  int32_t C;         /* components (args.num_components) */
+  int32_t depth;     /* args.coupling_network_depth (hidden->hidden layers) */
+  int32_t act;       /* GBNF_ACT_* (args.coupling_network) */
+  int32_t coupling;  /* GBNF_COUPLING_* (args.flow_coupling, glow only) */
+  int32_t base;      /* GBNF_BASE_* */
+  int32_t gemm_mode; /* GBNF_GEMM_* */
+  int32_t device;    /* CUDA device ordinal */
+  int32_t reserved;
+} gbnf_config;
+
+/* Raw fp32 parameters of ONE coupling step, as they sit in the reference modules' tensors (device pointers).
+ * Glow  (models/glow.py:265-308): an_bias/an_logs = ActNorm1d.bias/logs [D]; perm = Permute1d.indices int64 [D]
+ *        (NOT in state_dict, models/layers.py:637); net 0 = block.network Linear layers.
+ * RealNVP (models/realnvp.py:35-76): net 0 = t_net (flow_param[k][0]), net 1 = s_net (flow_param[k][1]);
+ *        bn_* = flow_param[k][2] (log_gamma, beta, running_mean, running_var) or all NULL.
+ * W[n][l] is nn.Linear.weight [out_features, in_features] row-major, b[n][l] its bias; l = 0 .. depth+1. */
+typedef struct {
+  const float* an_bias;
+  const float* an_logs;
+  const int64_t* perm;
+  const float* bn_log_gamma;
+  const float* bn_beta;
+  const float* bn_mean;
+  const float* bn_var;
+  const float* W[2][GBNF_MAX_LAYERS];
+  const float* b[2][GBNF_MAX_LAYERS];
+} gbnf_step_params;
+
+typedef struct {
+  int32_t flip_init;             /* RealNVPFlow(flip_init=c), models/boosted_flow.py:46 */
+  int32_t n_steps;               /* must equal config.K */
+  const gbnf_step_params* steps; /* HOST array of n_steps entries holding DEVICE pointers */
+} gbnf_component_params;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+/* Replaces BoostedFlow.__init__'s device-side state (models/boosted_flow.py:22-50). */
+int gbnf_create(gbnf_handle* out, const gbnf_config* cfg);
+void gbnf_destroy(gbnf_handle h);
+const char* gbnf_last_error(void);
+int gbnf_abi_version(void);
+
+/* Re-tile one component's parameters into the handle's packed blob (device -> device, async on `stream`).
+ * Call after construction, after every load() (utils/utilities.py:42-75) and whenever a component's
+ * parameters changed before it is evaluated as a fixed component. */
+int gbnf_pack_component(gbnf_handle h, int32_t c, const gbnf_component_params* p, void* stream);
+
+/* Toy path base density Normal(mean[D], scale[D]) (models/generative_flow.py:22-23,38-42). Device pointers. */
+int gbnf_set_base(gbnf_handle h, const float* d_mean, const float* d_scale, void* stream);
+
+/* ---- the hot path ----------------------------------------------------------------------------------- */
+/* log q_c(x) for c in [c0, c1): replaces the loop `model(x=x, components=c)` + log_normal_standard(z)+ldj
+ * (density_experiment.py:613-616, models/boosted_flow.py:220-228, models/glow.py:92-110,
+ * models/realnvp.py:115-127).  d_logq is [B, c1-c0].  d_z_opt [B, D] / d_ldj_opt [B] (may be NULL) receive the
+ * flow output of component c0 and require c1 == c0+1 (the 5-tuple's z and log_det_j). */
+int gbnf_component_logq(gbnf_handle h, const float* d_x, int64_t B, int32_t c0, int32_t c1, float* d_logq,
+                        float* d_z_opt, float* d_ldj_opt, void* stream);
+
+/* Mixture log-density from materialised per-component log q (d_logq is [B, ld], first n_comp columns used):
+ * the 2-term logsumexp recursion of density_experiment.py:612-622 / :561-571 evaluated in its flat form
+ * G = logsumexp_c(coef_c + logq_c).  d_rho is the RAW rho buffer [>= n_comp] (device);
+ * skip_c >= 0 leaves that component out as toy_experiment.py:414-417 does (-1: none);
+ * mix_mode GBNF_MIX_RAW_RHO reproduces BoostedFlow._rho_gradients (models/boosted_flow.py:124-134).
+ * n_comp == 0 writes zeros (density_experiment.py:612). */
+int gbnf_mixture_logdensity(gbnf_handle h, const float* d_logq, int64_t B, int32_t ld, int32_t n_comp,
+                            const float* d_rho, int32_t skip_c, int32_t mix_mode, float* d_G_ll, void* stream);
+
+/* Single-pass fused path: components [0, n_comp) + mixture; the [B, C] matrix never goes to HBM unless
+ * d_logq_opt (ld = n_comp) is given.  Also leaves the batch softmax statistics of -G_ll (max, sum exp) in the
+ * handle so that a following gbnf_boost_weights on the same d_G_ll needs no extra reduction pass. */
+int gbnf_fused_eval(gbnf_handle h, const float* d_x, int64_t B, int32_t n_comp, const float* d_rho,
+                    int32_t skip_c, int32_t mix_mode, float* d_G_ll, float* d_logq_opt, void* stream);
+
+/* Boosting weights (utils/utilities.py:12-14 + density_experiment.py:627-641; toy_experiment.py:440,453-459):
+ * w = softmax_B(-G_ll); density: if max w > clamp_hi: clip to [clamp_lo, clamp_hi]; if sum != 1: renormalise.
+ * toy: renormalise; if max w > clamp_hi: clip, renormalise.   d_stats (device, 4 floats, may be NULL) receives
+ * {max_B(-G_ll), sum_B exp(-G_ll - max), clamped flag, sum w before the final renormalisation}. */
+int gbnf_boost_weights(gbnf_handle h, const float* d_G_ll, int64_t B, float clamp_lo, float clamp_hi,
+                       int32_t mode, float* d_w, float* d_stats, void* stream);
+
+/* The same in three stages, for batch-parallel multi-GPU runs where the two batch reductions are all-reduced
+ * between the stages by the caller (torch.distributed / NCCL):
+ *   stage 1: d_ms[0] = max_B(-G_ll), d_ms[1] = sum_B exp(-G_ll - d_ms[0])               (local shard)
+ *   stage 2: w from global (max, sum); clamp decision from the global sum; d_wsum[0] = local sum of w (fp64)
+ *   stage 3: w *= 1/d_wsum[0] when d_wsum[0] != 1                                         (global sum) */
+int gbnf_weight_stats(gbnf_handle h, const float* d_G_ll, int64_t B, float* d_ms, void* stream);
+int gbnf_weight_apply(gbnf_handle h, const float* d_G_ll, int64_t B, const float* d_ms, float clamp_lo,
+                      float clamp_hi, int32_t mode, float* d_w, double* d_wsum, void* stream);
+int gbnf_weight_renorm(gbnf_handle h, float* d_w, int64_t B, const double* d_wsum, int32_t mode, void* stream);
+
+/* Inverse-CDF resampling, the contract that pins torch.multinomial(w, B, replacement=True)
+ * (density_experiment.py:643): idx[i] = #{k : cum_k < u_i}, cum = cumsum_fp64(w) / sum_fp64(w).
+ * d_u: float64 uniforms [n] (device). */
+int gbnf_resample(gbnf_handle h, const float* d_w, int64_t B, const double* d_u, int64_t n, int64_t* d_idx,
+                  void* stream);
+
+/* x_resampled = x[idx] (density_experiment.py:644). d_out [n, D]. */
+int gbnf_gather_rows(gbnf_handle h, const float* d_x, int32_t D, const int64_t* d_idx, int64_t n, float* d_out,
+                     void* stream);
+
+/* Host helper: component id under the same CDF rule for "1:c" / "1:c-1" / "-c" (models/boosted_flow.py:76-91).
+ * rho_host is a HOST array; exclude >= 0 zeroes that entry first. */
+int gbnf_sample_component(const float* rho_host, int32_t n, double u, int32_t exclude, int32_t* j_out);
+
+/* ---- introspection (tests, bench) ------------------------------------------------------------------- */
+typedef struct {
+  int32_t gemm_mode;       /* as configured */
+  int32_t rows_per_cta;    /* row-tile height of the coupling kernel */
+  int32_t smem_bytes;      /* dynamic shared memory per CTA */
+  int32_t tmem_cols;       /* TMEM columns allocated per CTA (0 for the fp32 path) */
+  int32_t num_sms;         /* SMs on the device */
+  int32_t grid;            /* CTAs launched by the last coupling launch */
+  int64_t packed_bytes;    /* size of the packed parameter blob */
+  int64_t launches;        /* kernels launched through this handle so far */
+} gbnf_info;
+int gbnf_get_info(gbnf_handle h, gbnf_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBNF_H_ */

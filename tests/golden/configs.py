@@ -1,0 +1,11 @@
+"""Fixture configurations shared by make_golden.py (needs the reference) and the tests (do not)."""
+
+CONFIGS = {
+    # name: (args kwargs, seed, B, toy_base)
+    "glow_d43": (dict(kind="glow", D=43, C=3, K=2, h=64), 1, 192, False),
+    "glow_d6_additive_relu": (dict(kind="glow", D=6, C=2, K=3, h=64, flow_coupling="additive", coupling_network="relu",
+                                   flow_permutation="reverse"), 2, 160, False),
+    "realnvp_d6_bn": (dict(kind="realnvp", D=6, C=4, K=5, h=64, batch_norm=True), 3, 200, False),
+    "realnvp_d5_mixed": (dict(kind="realnvp", D=5, C=3, K=4, h=64, coupling_network="mixed"), 4, 130, False),
+    "toy_d2": (dict(kind="realnvp", D=2, C=8, K=1, h=64, rho_init="uniform"), 5, 100, True),
+}

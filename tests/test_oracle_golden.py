@@ -1,0 +1,118 @@
+"""The CPU oracle against the fixtures produced by the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES
+from helpers import golden_model, rel_err
+from oracle import gbnf_oracle as orc
+
+DENSITY_CASES = [c for c in GOLDEN_CASES if c != "toy_d2"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_component_forward_fp32(golden, name):
+    g = golden(name); md = golden_model(g)
+    x = g["x"]
+    for c in range(md["C"]):
+        z, ldj = orc.component_forward(md, x, c)
+        assert z.dtype == np.float32
+        np.testing.assert_allclose(z, g["z32"][c], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(ldj, g["ldj32"][c], rtol=2e-5, atol=2e-5)
+        lq = orc.component_logq(md, x, c)
+        assert rel_err(lq, g["logq32"][:, c]) < 5e-6
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_component_forward_fp64_ground_truth(golden, name):
+    g = golden(name); md = orc.cast_model(golden_model(g), np.float64)
+    lq = orc.all_component_logq(md, g["x"].astype(np.float64))
+    assert rel_err(lq, g["logq64"]) < 1e-7   # see log_normal_standard: the reference's .double() run is fp32-contaminated
+
+
+@pytest.mark.parametrize("name", DENSITY_CASES)
+def test_mixture_weights_resample_objective(golden, name):
+    g = golden(name); md = golden_model(g)
+    x = g["x"]
+    tags = sorted({k.rsplit(".", 1)[0] for k in g if k.startswith("kl.")})
+    assert tags
+    for tag in tags:
+        comp = int(tag.split(".")[1][1:]); all_tr = bool(int(tag.split(".")[2][1:]))
+        logq = g["logq32"]
+        G = orc.mixture_recursion(logq, md["rho"], comp)
+        np.testing.assert_allclose(G, g[tag + ".G_ll"], rtol=2e-6, atol=2e-6)
+        # flat closed form == recursion
+        np.testing.assert_allclose(orc.mixture_flat(logq, md["rho"], comp), g[tag + ".G_ll"], rtol=1e-5, atol=1e-5)
+        w = orc.boost_weights(g[tag + ".G_ll"], "density")
+        e = np.exp(-g[tag + ".G_ll"] - np.max(-g[tag + ".G_ll"]))
+        assert bool(np.max(e / np.sum(e)) > 0.1) == bool(g[tag + ".clamped"])
+        np.testing.assert_allclose(w, g[tag + ".w"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(orc.boost_weights(g[tag + ".G_flat"], "density"), g[tag + ".w_flat"], rtol=1e-5, atol=1e-9)
+        # resampling: bit-exact on the reference's own weights and uniforms
+        assert np.array_equal(orc.resample_indices(g[tag + ".w"], g[tag + ".u"]), g[tag + ".idx"])
+        out = orc.compute_kl_pq_loss(md, x, comp, all_tr, u=g[tag + ".u"])
+        assert np.array_equal(out["idx"], g[tag + ".idx"])
+        for k in ("nll", "G_nll", "g_nll"):
+            assert abs(float(out[k]) - float(g[tag + "." + k])) < 2e-5 * max(1.0, abs(float(g[tag + "." + k])))
+
+
+@pytest.mark.parametrize("name", DENSITY_CASES)
+def test_evaluate_and_rho_gradients(golden, name):
+    g = golden(name); md = golden_model(g)
+    x = g["x"]; B = x.shape[0]
+    tags = sorted({k.rsplit(".", 1)[0] for k in g if k.startswith("eval.")})
+    for tag in tags:
+        comp = int(tag.split(".")[1][1:]); all_tr = bool(int(tag.split(".")[2][1:]))
+        ev = orc.evaluate(md, [x[:B // 2], x[B // 2:]], comp, all_tr)
+        for k in ("nll", "g_nll", "ratio"):
+            assert abs(ev[k] - float(g[tag + "." + k])) < 2e-5 * max(1.0, abs(float(g[tag + "." + k])))
+    C = md["C"]
+    full = orc.mixture_recursion(g["logq32"], md["rho"], C, normalized=False)
+    fixed = orc.mixture_recursion(g["logq32"], md["rho"], C - 1, normalized=False)
+    np.testing.assert_allclose(full, g["rhograd.full"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(fixed, g["rhograd.fixed"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(g["logq32"][:, C - 1], g["rhograd.new"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(orc.mixture_flat(g["logq32"], md["rho"], C, normalized=False), g["rhograd.full"], rtol=1e-5, atol=1e-5)
+
+
+def test_toy_objective(golden):
+    g = golden("toy_d2"); md = golden_model(g)
+    assert md["base_mean"] is not None
+    x = g["x"]
+    tags = sorted({k.rsplit(".", 1)[0] for k in g if k.startswith("toykl.")})
+    assert len(tags) == 2
+    for tag in tags:
+        comp = int(tag.split(".")[1][1:]); all_tr = bool(int(tag.split(".")[2][1:]))
+        bs = int(g[tag + ".batch_size"])
+        n, skip = (md["C"], comp) if all_tr else (comp, -1)
+        G = orc.mixture_recursion(g["logq32"], md["rho"], n, skip)
+        np.testing.assert_allclose(G, g[tag + ".G_ll"], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(orc.mixture_flat(g["logq32"], md["rho"], n, skip), g[tag + ".G_ll"], rtol=1e-5, atol=1e-5)
+        w = orc.boost_weights(g[tag + ".G_ll"], "toy", bs)
+        np.testing.assert_allclose(w, g[tag + ".w"], rtol=1e-5, atol=1e-9)
+        assert np.array_equal(orc.resample_indices(g[tag + ".w"], g[tag + ".u"]), g[tag + ".idx"])
+        out = orc.compute_kl_pq_loss(md, x, comp, all_tr, u=g[tag + ".u"], mode="toy", batch_size=bs)
+        for k in ("nll", "G_nll", "g_nll"):
+            assert abs(float(out[k]) - float(g[tag + "." + k])) < 2e-5 * max(1.0, abs(float(g[tag + "." + k])))
+
+
+def test_properties():
+    rng = np.random.default_rng(0)
+    logq = rng.standard_normal((500, 6)).astype(np.float32) * 5 - 30
+    rho = np.array([1, .5, .25, .125, .0625, .05], dtype=np.float32)
+    coef = orc.mixture_log_coefficients(rho, 6)
+    assert abs(np.sum(np.exp(coef)) - 1.0) < 1e-12                      # simplex weights
+    np.testing.assert_allclose(np.exp(coef), rho.astype(np.float64) / rho.astype(np.float64).sum(), rtol=1e-12)
+    w = orc.boost_weights(orc.mixture_recursion(logq, rho, 6))
+    assert abs(w.sum() - 1) < 1e-5 and w.min() > 0
+    u = np.sort(rng.random(500))
+    idx = orc.resample_indices(w, u)
+    assert np.all(np.diff(idx) >= 0) and idx.min() >= 0 and idx.max() < 500
+    assert orc.sample_component(rho, 3, 0.0) == 0 and orc.sample_component(rho, 3, 0.999999) == 2
+    assert orc.sample_component(rho, 6, 0.3, exclude=0) != 0
+    # synthetic-model constructor gives a usable model
+    md = orc.make_synthetic_model("glow", 7, 2, 2, 16, seed=3, init_rows=64)
+    lq = orc.all_component_logq(md, rng.standard_normal((5, 7)).astype(np.float32))
+    assert lq.shape == (5, 2) and np.all(np.isfinite(lq))
+    md2 = orc.unflatten_model(orc.flatten_model(md))
+    np.testing.assert_array_equal(orc.all_component_logq(md2, np.ones((3, 7), np.float32)),
+                                  orc.all_component_logq(md, np.ones((3, 7), np.float32)))
