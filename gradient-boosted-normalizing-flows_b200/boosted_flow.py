@@ -329,6 +329,11 @@ class BoostedFlow(nn.Module):
         _lib.check(_lib.load().gbnf_get_info(self.handle(), C.byref(inf)))
         return {n: getattr(inf, n) for n, _ in _lib.Info._fields_}
 
+    def profile(self):
+        buf = (C.c_int64 * 32)()
+        _lib.check(_lib.load().gbnf_get_profile(self.handle(), buf))
+        return list(buf)
+
     # ------------------------------------------------------------------ rho update (models/boosted_flow.py:119-207)
     @torch.no_grad()
     def _rho_gradients(self, x):

@@ -60,6 +60,7 @@ struct CouplingArgs {
   ModelDims md;
   int num_tiles;
   int* error_flag;                 // device int, set non-zero on an internal timeout (f16 path)
+  long long* prof;                 // optional cycle counters (CTA 0), see gbnf_get_profile
 };
 
 // ---- device helpers ------------------------------------------------------------------------------------

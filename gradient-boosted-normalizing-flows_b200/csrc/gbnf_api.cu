@@ -61,6 +61,7 @@ struct gbnf_ctx {
   double* tile_offs = nullptr;   // [cap_tiles + 1]
   long long cum_cap = 0;
   int* flags = nullptr;          // [0] kernel error flag, [1] fp16 overflow flag
+  long long* prof = nullptr;     // [32] cycle counters written by CTA 0 of the tensor-core kernel
   // coupling launch plan
   int rows_per_cta = 0, ld = 0, out_max = 0, tmem_cols = 0;
   size_t smem_bytes = 0;
@@ -78,7 +79,7 @@ int plan_layout(gbnf_ctx* h) {
   md.act = c.act; md.coupling = c.coupling; md.base = c.base;
   md.nlayers = c.depth + 2;
   md.nnets = (c.kind == GBNF_KIND_REALNVP) ? 2 : 1;
-  const bool f16 = (c.gemm_mode == GBNF_GEMM_F16_TC);
+  const bool f16 = (c.gemm_mode != GBNF_GEMM_FP32);
   const int kq = f16 ? 16 : kF32KT, nq = f16 ? 16 : kF32NT;
   const int h0 = c.D / 2, h1 = c.D - h0;
   long long f = 0, i = 0, w = 0;   // running offsets (floats / ints / weight elements)
@@ -132,6 +133,7 @@ int plan_layout(gbnf_ctx* h) {
   } else {
     std::string why;
     if (!tc_make_plan(md, h->steps_h, &h->tc, &why)) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: " + why);
+    h->tc.tanh_mode = (c.gemm_mode == GBNF_GEMM_F16_TC_FAST) ? 0 : 1;
     h->rows_per_cta = 128;
     h->smem_bytes = h->tc.smem_bytes;
     h->tmem_cols = h->tc.tmem_cols;
@@ -167,6 +169,7 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
   a.rho = rho; a.n_mix = n_mix; a.skip_c = skip_c; a.mix_mode = mix_mode; a.G_ll = G_ll;
   a.steps = h->steps_d; a.comps = h->comps_d; a.fblob = h->fblob; a.iblob = h->iblob; a.wblob = h->wblob; a.md = h->md;
   a.error_flag = h->flags;
+  a.prof = h->prof;
   const int R = h->rows_per_cta;
   a.num_tiles = (int)((B + R - 1) / R);
   const int grid = std::min(a.num_tiles, h->num_sms);
@@ -202,7 +205,7 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   if (c.act < 0 || c.act > 2 || c.coupling < 0 || c.coupling > 1 || c.base < 0 || c.base > 1)
     return fail(GBNF_ERR_INVALID, "bad act / coupling / base");
   if (c.act == GBNF_ACT_MIXED && c.kind != GBNF_KIND_REALNVP) return fail(GBNF_ERR_INVALID, "mixed nets are RealNVP only");
-  if (c.gemm_mode != GBNF_GEMM_FP32 && c.gemm_mode != GBNF_GEMM_F16_TC) return fail(GBNF_ERR_INVALID, "bad gemm_mode");
+  if (c.gemm_mode < GBNF_GEMM_FP32 || c.gemm_mode > GBNF_GEMM_F16_TC_FAST) return fail(GBNF_ERR_INVALID, "bad gemm_mode");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -239,11 +242,15 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   CREATE_TRY(cudaMalloc(&h->wsum, sizeof(double)));
   CREATE_TRY(cudaMalloc(&h->flags, 2 * sizeof(int)));
   CREATE_TRY(cudaMemset(h->flags, 0, 2 * sizeof(int)));
+  CREATE_TRY(cudaMalloc(&h->prof, 32 * sizeof(long long)));
+  CREATE_TRY(cudaMemset(h->prof, 0, 32 * sizeof(long long)));
   CREATE_TRY(cudaMemcpy(h->comps_d, h->comps_h.data(), h->comps_h.size() * sizeof(CompDesc), cudaMemcpyHostToDevice));
   if (c.gemm_mode == GBNF_GEMM_FP32) {
-    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    // the attribute is per FUNCTION, shared by all handles in the process: always raise it to the device maximum
+    const int max_smem = 227 * 1024;
+    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   } else {
     CREATE_TRY(tc_configure(h->tc));
   }
@@ -257,7 +264,7 @@ void gbnf_destroy(gbnf_handle h) {
   cudaSetDevice(h->cfg.device);
   cudaFree(h->steps_d); cudaFree(h->comps_d); cudaFree(h->fblob); cudaFree(h->iblob); cudaFree(h->wblob);
   cudaFree(h->step_params_d); cudaFree(h->partial); cudaFree(h->ticket); cudaFree(h->ms); cudaFree(h->wsum);
-  cudaFree(h->cum); cudaFree(h->tile_sums); cudaFree(h->tile_offs); cudaFree(h->flags);
+  cudaFree(h->cum); cudaFree(h->tile_sums); cudaFree(h->tile_offs); cudaFree(h->flags); cudaFree(h->prof);
   delete h;
 }
 
@@ -281,7 +288,7 @@ int gbnf_pack_component(gbnf_handle h, int32_t c, const gbnf_component_params* p
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const ModelDims& md = h->md;
-  const bool f16 = (h->cfg.gemm_mode == GBNF_GEMM_F16_TC);
+  const bool f16 = (h->cfg.gemm_mode != GBNF_GEMM_FP32);
   StepDesc* sd_h = &h->steps_h[(size_t)c * md.K];
   for (int k = 0; k < md.K; ++k) {
     const gbnf_step_params& sp = p->steps[k];
@@ -338,7 +345,8 @@ int gbnf_component_logq(gbnf_handle h, const float* d_x, int64_t B, int32_t c0, 
   if (!h) return fail(GBNF_ERR_INVALID, "null handle");
   if (B < 0 || c0 < 0 || c1 > h->cfg.C || c0 >= c1) return fail(GBNF_ERR_INVALID, "bad B or component range");
   if ((d_z_opt || d_ldj_opt) && c1 != c0 + 1) return fail(GBNF_ERR_INVALID, "z / ldj outputs need a single component");
-  if (B > 0 && !d_x) return fail(GBNF_ERR_INVALID, "null x");
+  if (B == 0) return GBNF_OK;   // empty batch: nothing to do (pointers of empty tensors may be NULL)
+  if (!d_x) return fail(GBNF_ERR_INVALID, "null x");
   if (!d_logq && !d_z_opt && !d_ldj_opt) return fail(GBNF_ERR_INVALID, "no output requested");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   return launch_coupling(h, d_x, B, c0, c1, d_logq, c1 - c0, d_z_opt, d_ldj_opt, nullptr, 0, -1, 0, nullptr,
@@ -469,6 +477,13 @@ int gbnf_sample_component(const float* rho_host, int32_t n, double u, int32_t ex
     if (run / total < u) j = i + 1; else break;
   }
   *j_out = std::min(j, n - 1);
+  return GBNF_OK;
+}
+
+int gbnf_get_profile(gbnf_handle h, int64_t* out32) {
+  if (!h || !out32) return fail(GBNF_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpy(out32, h->prof, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
   return GBNF_OK;
 }
 

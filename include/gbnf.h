@@ -45,7 +45,9 @@ enum { GBNF_COUPLING_AFFINE = 0, GBNF_COUPLING_ADDITIVE = 1 };     /* models/glo
 enum { GBNF_BASE_STD_NORMAL = 0, GBNF_BASE_DIAG_NORMAL = 1 };     /* utils/distributions.py:44 | generative_flow.py:38-42 */
 enum {
   GBNF_GEMM_FP32 = 0,  /* CUDA-core fp32 FMA, libm-accurate tanh: reference-class numerics (~1e-6 rel)          */
-  GBNF_GEMM_F16_TC = 1 /* tcgen05 tensor cores, fp16 operands, fp32 accumulate in TMEM (<=1e-4 rel on log q)    */
+  GBNF_GEMM_F16_TC = 1, /* tcgen05 tensor cores, fp16 operands, fp32 accumulate in TMEM, tanh via ex2+rcp
+                           (abs err ~1e-7): <= 1e-4 rel on log q                                                   */
+  GBNF_GEMM_F16_TC_FAST = 2 /* same GEMMs, tanh.approx.f32 (one MUFU op, rel err 2^-11): <= 2e-4 rel on log q      */
 };
 enum { GBNF_WEIGHTS_DENSITY = 0, GBNF_WEIGHTS_TOY = 1 }; /* density_experiment.py:627-641 | toy_experiment.py:440-459 */
 enum { GBNF_MIX_SIMPLEX = 0, GBNF_MIX_RAW_RHO = 1 };     /* density_experiment.py:618 | models/boosted_flow.py:132-133 */
@@ -170,6 +172,11 @@ typedef struct {
   int64_t launches;        /* kernels launched through this handle so far */
 } gbnf_info;
 int gbnf_get_info(gbnf_handle h, gbnf_info* out);
+
+/* Cycle counters of CTA 0 of the last tensor-core coupling launch (synchronises the device; diagnostics only):
+ * [0..7] MMA warp: total, wait a_ready, wait weights, issue; [8..15] epilogue thread 0: total, wait accumulator,
+ * hidden epilogues, last-layer/coupling, prologue (load/affine/gather); [16..] producer: total, wait empty. */
+int gbnf_get_profile(gbnf_handle h, int64_t* out32);
 
 #ifdef __cplusplus
 }

@@ -439,3 +439,98 @@ def make_synthetic_model(kind, D, C, K, h, seed=1, depth=1, act="tanh", coupling
             steps.append(st)
         model["components"].append({"flip_init": c, "steps": steps})
     return model
+
+
+# --------------------------------------------------------------------------------------
+# torch-CPU execution of the same restatement (timing arm only).
+# The reference IS PyTorch ops on the CPU (nn.Linear -> addmm/MKL, torch.tanh, torch.logsumexp); numpy's tanh and
+# BLAS are slower than torch's, so bench.py's reference arm / cpu_baseline time THIS variant to give the reference
+# the speed it really has on the host.  tests/test_oracle_golden.py checks it against the numpy functions above.
+# --------------------------------------------------------------------------------------
+def to_torch_model(model):
+    import torch
+
+    def cv(v):
+        if isinstance(v, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(v))
+        if isinstance(v, dict):
+            return {k: cv(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return type(v)(cv(x) for x in v)
+        return v
+    return cv(model)
+
+
+def torch_component_logq(tm, x, c):
+    """Same math as component_logq(), torch CPU tensors, no autograd (call under torch.no_grad())."""
+    import torch
+    import torch.nn.functional as F
+    comp = tm["components"][c]
+    D = x.shape[1]
+    h0 = D // 2
+    act = tm.get("act", "tanh")
+
+    def net(v, layers, a):
+        fn = torch.tanh if a == "tanh" else torch.relu
+        v = F.linear(v, layers[0][0], layers[0][1])
+        for W, b in layers[1:]:
+            v = F.linear(fn(v), W, b)
+        return v
+    z = x
+    ldj = torch.zeros(x.shape[0], dtype=x.dtype)
+    for k, st in enumerate(comp["steps"]):
+        if tm["kind"] == "glow":
+            y = (z + st["an_bias"]) * torch.exp(st["an_logs"])
+            ldj = ldj + st["an_logs"].sum()
+            y = y[:, st["perm"]]
+            z1, z2 = y[:, :h0], y[:, h0:]
+            hh = net(z1, st["net"], act)
+            if tm.get("coupling", "affine") == "additive":
+                z2 = z2 + hh
+            else:
+                scale = torch.sigmoid(hh[:, 1::2] + 2.0)
+                z2 = (z2 + hh[:, 0::2]) * scale
+                ldj = ldj + torch.log(scale).sum(1)
+            z = torch.cat([z1, z2], 1)
+        else:
+            if st.get("bn") is not None:
+                bn = st["bn"]
+                z = torch.exp(bn["log_gamma"]) * ((z - bn["mean"]) / torch.sqrt(bn["var"] + BN_EPS)) + bn["beta"]
+                ldj = ldj + (bn["log_gamma"] - 0.5 * torch.log(bn["var"] + BN_EPS)).sum()
+            if ((k + comp["flip_init"]) % 2) > 0:
+                z2, z1 = z[:, :h0], z[:, h0:]
+            else:
+                z1, z2 = z[:, :h0], z[:, h0:]
+            shift = net(z1, st["t"], "relu" if act == "mixed" else act)
+            scale = net(z1, st["s"], "tanh" if act == "mixed" else act)
+            z = torch.cat([z1, shift + z2 * torch.exp(scale)], 1)
+            ldj = ldj + scale.sum(1)
+    if tm.get("base_mean") is not None:
+        var = tm["base_scale"] ** 2
+        lp = -((z - tm["base_mean"]) ** 2) / (2 * var) - torch.log(tm["base_scale"]) - math.log(math.sqrt(2 * math.pi))
+        return lp.sum(1) + ldj
+    return (-0.5 * LOG_2PI - 0.5 * z * z).sum(1) + ldj
+
+
+def torch_density_step(tm, x):
+    """One hot-path step as the reference executes it: C component passes, the 2-term logsumexp recursion
+    (density_experiment.py:612-622), softmax weights with clamp / renormalise (:627-641).  Returns (G_ll, w)."""
+    import torch
+    C = tm["C"]
+    rho = tm["rho"]
+    G = None
+    for c in range(C):
+        lq = torch_component_logq(tm, x, c)
+        if c == 0:
+            G = lq
+        else:
+            r = rho[c] / rho[: c + 1].sum()
+            G = torch.logsumexp(torch.stack([torch.log(1 - r) + G, torch.log(r) + lq], 1), 1)
+    u = -G
+    e = torch.exp(u - u.max())
+    w = e / e.sum()
+    if w.max() > 0.1:
+        w = torch.clamp(w, 0.01, 0.1)
+    if w.sum() != 1.0:
+        w = w / w.sum()
+    return G, w

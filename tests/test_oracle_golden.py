@@ -116,3 +116,18 @@ def test_properties():
     md2 = orc.unflatten_model(orc.flatten_model(md))
     np.testing.assert_array_equal(orc.all_component_logq(md2, np.ones((3, 7), np.float32)),
                                   orc.all_component_logq(md, np.ones((3, 7), np.float32)))
+
+
+def test_torch_timing_variant_matches_numpy_oracle(golden):
+    import torch
+    for name in ("glow_d43", "realnvp_d6_bn", "realnvp_d5_mixed", "glow_d6_additive_relu"):
+        g = golden(name); md = golden_model(g)
+        tm = orc.to_torch_model(md)
+        x = torch.from_numpy(g["x"])
+        with torch.no_grad():
+            lq = torch.stack([orc.torch_component_logq(tm, x, c) for c in range(md["C"])], 1).numpy()
+            G, w = orc.torch_density_step(tm, x)
+        assert rel_err(lq, g["logq32"]) < 5e-6
+        Gn = orc.mixture_recursion(g["logq32"], md["rho"], md["C"])
+        np.testing.assert_allclose(G.numpy(), Gn, rtol=5e-6, atol=5e-6)
+        np.testing.assert_allclose(w.numpy(), orc.boost_weights(Gn), rtol=2e-4, atol=1e-9)
