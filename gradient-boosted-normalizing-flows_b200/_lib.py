@@ -42,7 +42,8 @@ class ComponentParams(C.Structure):
 
 class Info(C.Structure):
     _fields_ = [("gemm_mode", C.c_int32), ("rows_per_cta", C.c_int32), ("smem_bytes", C.c_int32), ("tmem_cols", C.c_int32),
-                ("num_sms", C.c_int32), ("grid", C.c_int32), ("packed_bytes", C.c_int64), ("launches", C.c_int64)]
+                ("num_sms", C.c_int32), ("grid", C.c_int32), ("packed_bytes", C.c_int64), ("launches", C.c_int64),
+                ("pipelined", C.c_int32), ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/gbnf.h one to one (tests/test_abi.py checks the two stay in sync)
@@ -66,6 +67,7 @@ SIGNATURES = {
     "gbnf_sample_component": (C.c_int, [C.POINTER(_f32), _i32, _f64, _i32, C.POINTER(_i32)]),
     "gbnf_get_info": (C.c_int, [_vp, C.POINTER(Info)]),
     "gbnf_get_profile": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "gbnf_get_trace": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
 }
 
 _LIB = None

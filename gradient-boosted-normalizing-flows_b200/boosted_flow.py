@@ -334,6 +334,11 @@ class BoostedFlow(nn.Module):
         _lib.check(_lib.load().gbnf_get_profile(self.handle(), buf))
         return list(buf)
 
+    def trace(self):
+        buf = (C.c_int64 * 256)()
+        _lib.check(_lib.load().gbnf_get_trace(self.handle(), buf))
+        return list(buf)
+
     # ------------------------------------------------------------------ rho update (models/boosted_flow.py:119-207)
     @torch.no_grad()
     def _rho_gradients(self, x):

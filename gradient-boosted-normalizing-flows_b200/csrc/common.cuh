@@ -9,6 +9,7 @@ namespace gbnf {
 
 constexpr int kMaxComponents = 256;   // coef table in shared memory
 constexpr int kMaxD = 256;
+constexpr int kEpPad = 64;             // padded length of the gather-order step tables
 
 // ---- packed parameter layout ---------------------------------------------------------------------------
 // One Linear layer of one coupling net (nn.Linear weight [N_out, K_in], models/layers.py:218-239).
@@ -16,8 +17,11 @@ constexpr int kMaxD = 256;
 //   f16 path  : wblob holds Kp/16 "k-slabs"; slab s is the UMMA canonical K-major no-swizzle image of
 //               W[0:Np, 16s:16s+16]:  [Np/8 row groups][2 k-chunks][8 rows][8 halves]  (SBO = 256 B, LBO = 128 B),
 //               Kp % 16 == 0, Np % 16 == 0, zero padded.  A slab is Np*32 bytes and is what one bulk-TMA moves.
+//               With NC < Np (pipelined kernel, coupling_tc2.cuh) the image is N-chunk major:
+//               [Np/NC chunks][Kp/16 k-slabs][NC x 16] with the same canonical layout inside each NC x 16 slab.
 struct LayerDesc {
   int K_in, N_out, Kp, Np;
+  int NC, pad_;      // N-chunk width of the f16 image (== Np for the single-chunk layout)
   long long w_off;   // element offset into wblob (float for fp32, __half for f16)
   long long b_off;   // float offset into fblob; Np entries, zero padded
 };
@@ -31,6 +35,11 @@ struct StepDesc {
   int pad_;
   long long vec_off;     // fblob: add[Dv] | mul[Dv] | off[Dv]  (physical column order), y = (z + add) * mul + off
   long long idx_off;     // iblob: idx1[in_dim] | idx2[out_dim]  physical columns of z1 / z2
+  // Branch-free tables of the pipelined tensor-core kernel, in GATHER order and padded to kEpPad entries:
+  //   fblob @ ep_off  : add1 | mul1 | off1 (z1 order) | add2 | mul2 | off2 (z2 order); padding has mul = 0 (yields 0)
+  //   iblob @ eidx_off: idx1p | idx2p; padding points at the scratch column D of the resident row
+  long long ep_off;
+  long long eidx_off;
   LayerDesc layer[2][GBNF_MAX_LAYERS];   // net 0: glow block / realnvp t_net; net 1: realnvp s_net
 };
 

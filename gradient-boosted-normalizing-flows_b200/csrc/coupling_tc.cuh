@@ -50,6 +50,9 @@ struct TcMisc {
   float part[kTcRows];
 };
 
+constexpr uint32_t kTcMiscBytes = 3072;   // >= sizeof(TcMisc), sizeof(Tc2Misc)
+static_assert(sizeof(TcMisc) <= kTcMiscBytes, "misc region too small");
+
 inline bool tc_make_plan(const ModelDims& md, const std::vector<StepDesc>& steps, TcPlan* p, std::string* why) {
   if (md.h % 64 != 0 || md.h > 512) { *why = "hidden width must be a multiple of 64 and <= 512 (use GBNF_GEMM_FP32 otherwise)"; return false; }
   if (md.D > kTcMaxD) { *why = "D must be <= 64"; return false; }
@@ -68,7 +71,7 @@ inline bool tc_make_plan(const ModelDims& md, const std::vector<StepDesc>& steps
   p->off_a0 = o;   o = al(o + (k0p / 16) * 4096);
   p->off_a1 = o;   o = al(o + (md.h / 16) * 4096);
   p->off_sh = o;   o = al(o + (md.nnets == 2 ? kTcRows * out_max * 4 : 0));
-  p->off_misc = o; o = al(o + (uint32_t)sizeof(TcMisc));
+  p->off_misc = o; o = al(o + kTcMiscBytes);
   p->off_ring = o;
   const uint32_t limit = 227 * 1024;
   if (o + 2 * kTcStageBytes > limit) { *why = "shared memory budget exceeded"; return false; }

@@ -1,0 +1,630 @@
+// Pipelined tcgen05 / TMEM / bulk-TMA coupling-stack kernel (GBNF_GEMM_F16_TC*, coupling_network_depth == 1,
+// hidden width a multiple of 128 up to 512).  Rows, activations and accumulators never leave the SM, and -- unlike
+// coupling_tc.cuh -- the hidden activations never touch SHARED memory either: they are packed to fp16 in place in
+// tensor memory and fed back to tcgen05.mma as the A operand from TMEM.  Shared memory then only carries the weight
+// stream (written once by TMA, read once by the tensor pipe), which is what bounds a 128-row tile on one SM
+// (measured: 128 B/clk of shared-memory bandwidth, 42 B/clk of L2->SM ingest, tools/tc_probe2.cu).
+//
+//   TMEM map (512 columns), T(q) = [128 q, 128 q + 128), q = 0..3, NQ = h / 128:
+//     layer 1 (K = |z1|, A0 from smem):  chunk q (128 columns) -> T(q); epilogue: tanh -> fp16 pairs -> T(q)[0:64]
+//                                        = k-quarter q of the layer-2 A operand ("A1"), leaving the hole H(q) = T(q)[64:128]
+//     layer 2 (K = h, A1 from TMEM):     64-column chunk j -> hole H(j mod 3); chunk 0 is accumulated k-quarter by
+//                                        k-quarter right behind the layer-1 epilogue, later chunks run up to three ahead
+//                                        of the epilogue;  epilogue: tanh -> fp16 pairs in place (hole[0:32])
+//                                        = k-piece j of the last layer's A operand
+//     last layer (N <= 64, A2 from TMEM): K-streamed piece by piece into H(3)
+//   Every reuse of a TMEM region is ordered either by the in-order tensor pipe or by an epilogue -> MMA mbarrier.
+//
+//   weights: layer 1 [128-col chunk][k-slab][128 x 16], layer 2 [64-col chunk][k-slab][64 x 16], last layer
+//   [k-slab][Np x 16], fp16 canonical K-major slabs; one ring stage (<= 16 KB) = one L1 chunk, one (chunk, k-quarter)
+//   of L2, or the 4 k-slabs of one last-layer piece.  Producer and MMA warp walk the same fixed schedule.
+//
+// Warp roles: warp 0 = TMA producer (+ L1 prefetch of the step's bias / table lines), warp 1 = MMA issuer (both run
+// warp-uniform control flow and issue from one elected lane, see ptx::elect_one), warps 2..9 = epilogue (two threads
+// per row, splitting every chunk's columns).
+#pragma once
+#include "coupling_tc.cuh"
+
+namespace gbnf {
+
+constexpr int kT2Chunk = 128;        // layer-1 chunk = k-quarter of layer 2
+constexpr int kT2Piece = 64;         // layer-2 chunk = k-piece of the last layer
+constexpr int kT2MaxStages = 12;
+constexpr uint32_t kT2TraceUnit = 37;
+
+struct Tc2Misc {
+  uint64_t full[kT2MaxStages];
+  uint64_t empty[kT2MaxStages];
+  uint64_t a0r;       // epilogue -> MMA : A0 written, every TMEM region of the previous pass drained        (8 arrivals)
+  uint64_t a1r[4];    // epilogue -> MMA : A1 k-quarter q packed into T(q)[0:64], hole H(q) free               (4 arrivals)
+  uint64_t sr[3];     // epilogue -> MMA : A2 piece stored in hole i, its accumulator drained                  (4 arrivals)
+  uint64_t l1f[4];    // MMA -> epilogue : layer-1 chunk q accumulated        (tcgen05.commit)
+  uint64_t l2f[3];    // MMA -> epilogue : layer-2 chunk in hole i accumulated
+  uint64_t l3f;       // MMA -> epilogue : last layer accumulated
+  uint32_t tmem_base;
+  uint32_t pad_;
+  float coef[kMaxComponents];
+  float part[kTcRows];
+  float part2[kTcRows];
+};
+
+static_assert(sizeof(Tc2Misc) <= kTcMiscBytes, "misc region too small");
+
+// Eligibility of a configuration for the pipelined kernel (host).
+inline bool tc2_eligible(const ModelDims& md, const std::vector<StepDesc>& steps) {
+  if (md.nlayers != 3 || md.h % kT2Chunk != 0 || md.h > 512 || md.D > kTcMaxD) return false;
+  for (const StepDesc& s : steps)
+    for (int n = 0; n < md.nnets; ++n) {
+      if (s.layer[n][0].Kp > 64) return false;          // one ring stage holds the k-slabs of a layer-1 chunk
+      if (s.layer[n][2].Np > 64) return false;          // last-layer accumulator is the 64-column hole H(3)
+    }
+  return true;
+}
+
+// Shared-memory plan of the pipelined kernel: no A1 image, the space goes to the weight ring.
+inline bool tc2_make_plan(const ModelDims& md, const std::vector<StepDesc>& steps, TcPlan* p) {
+  int k0p = 16, out_max = 1;
+  for (const StepDesc& s : steps) {
+    k0p = std::max(k0p, s.layer[0][0].Kp);
+    out_max = std::max(out_max, s.out_dim);
+  }
+  auto al = [](uint32_t v) { return (v + 127u) & ~127u; };
+  p->K0p = k0p; p->out_max = out_max;
+  uint32_t o = 0;
+  p->off_zs = o;   o = al(o + kTcRows * md.Dv * 4);
+  p->off_a0 = o;   o = al(o + (k0p / 16) * 4096);
+  p->off_a1 = o;   o = al(o + kTcRows * md.D * 4);       // here: the untransformed x tile (reloaded into zs per component)
+  p->off_sh = o;   o = al(o + (md.nnets == 2 ? kTcRows * out_max * 4 : 0));
+  p->off_misc = o; o = al(o + kTcMiscBytes);
+  p->off_ring = o;
+  const uint32_t limit = 227 * 1024;
+  p->nst = std::min<int>(kT2MaxStages, (limit - o) / kTcStageBytes);
+  p->smem_bytes = o + (size_t)p->nst * kTcStageBytes;
+  p->tmem_cols = 512;
+  return p->nst >= 2;
+}
+
+__device__ __forceinline__ uint32_t t2_hole(int i) { return 64u + 128u * (uint32_t)i; }
+
+// Epilogue warp -> MMA warp handoff: every lane has fenced its own writes, one lane arrives for the warp.
+__device__ __forceinline__ void t2_warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) ptx::mbar_arrive(bar);
+}
+// mbarrier wait polled by one lane per warp (256 spinning threads would compete with the MMA operand reads for shared memory)
+__device__ __forceinline__ void t2_wait(uint64_t* bar, uint32_t parity, int* err, int code, int lane) {
+  if (lane == 0) ptx::mbar_wait(bar, parity, err, code);
+  __syncwarp();
+}
+// the two epilogue warps that share a TMEM lane quadrant (= the two threads of every row in it)
+__device__ __forceinline__ void t2_pair_bar(int quad) { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); }
+
+// 32 accumulator values of one row -> bias + activation -> 16 packed fp16 pairs
+template <int ACT, int TANH_MODE>
+__device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const float* __restrict__ bias, uint32_t* p) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + 4 * q));
+    p[2 * q + 0] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 0]) + b.x),
+                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 1]) + b.y));
+    p[2 * q + 1] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 2]) + b.z),
+                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 3]) + b.w));
+  }
+}
+
+// PROF: per-role cycle counters of CTA 0 (gbnf_get_profile).  A clock64() costs ~30 cycles on the latency-bound single-warp
+// roles, so the counters are compiled out of the production instantiation.
+#define T2_CLOCK() (PROF ? clock64() : 0LL)
+// event trace of ONE coupling pass (unit kT2TraceUnit of CTA 0): a.prof[32 + id] = clock64(), see tools/tc_trace.py
+#define T2_TRACE(id) do { if (PROF && a.prof != nullptr && blockIdx.x == 0 && units == kT2TraceUnit && lane == 0) a.prof[32 + (id)] = clock64(); } while (0)
+template <int TANH_MODE, bool PROF>
+__global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArgs a, TcPlan plan) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const ModelDims& md = a.md;
+  const int D = md.D, Dv = md.Dv;
+  float* zs = reinterpret_cast<float*>(smem + plan.off_zs);
+  unsigned char* A0 = smem + plan.off_a0;
+  float* xs = reinterpret_cast<float*>(smem + plan.off_a1);
+  float* sh = reinterpret_cast<float*>(smem + plan.off_sh);
+  Tc2Misc* misc = reinterpret_cast<Tc2Misc*>(smem + plan.off_misc);
+  unsigned char* ring = smem + plan.off_ring;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nst = plan.nst;
+  const int NQ = md.h / kT2Chunk;          // layer-1 chunks = k-quarters of layer 2
+  const int NJ = md.h / kT2Piece;          // layer-2 chunks = k-pieces of the last layer
+  const int hs = md.h >> 4;                // k-slabs of the h x h layer
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nst; ++i) { ptx::mbar_init(&misc->full[i], 1); ptx::mbar_init(&misc->empty[i], 1); }
+    ptx::mbar_init(&misc->a0r, 8);
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&misc->a1r[i], 4); ptx::mbar_init(&misc->l1f[i], 1); }
+    for (int i = 0; i < 3; ++i) { ptx::mbar_init(&misc->sr[i], 4); ptx::mbar_init(&misc->l2f[i], 1); }
+    ptx::mbar_init(&misc->l3f, 1);
+    ptx::fence_mbar_init();
+    if (a.G_ll != nullptr) mixture_coefficients(a.rho, a.n_mix, a.skip_c, a.mix_mode, misc->coef);
+  }
+  if (warp == 1) ptx::tmem_alloc(&misc->tmem_base, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tbase = misc->tmem_base;
+  const __half* wb = reinterpret_cast<const __half*>(a.wblob);
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================================
+    uint32_t sidx = 0, par = 0;
+    int slot = 0;                                    // ring position kept incrementally: a runtime % or / costs ~100 cycles
+    const long long p_t0 = T2_CLOCK();                // on this single latency-bound warp
+    long long p_wait = 0;
+    auto push = [&](const __half* src, uint32_t bytes) {
+      const long long tw = T2_CLOCK();
+      t2_wait(&misc->empty[slot], par ^ 1u, a.error_flag, 10, lane);
+      p_wait += T2_CLOCK() - tw;
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(&misc->full[slot], bytes);
+        ptx::tma_bulk_g2s(ring + (size_t)slot * kTcStageBytes, src, bytes, &misc->full[slot]);
+      }
+      __syncwarp();
+      ++sidx;
+      if (++slot == nst) { slot = 0; par ^= 1u; }
+    };
+    // pull `bytes` at `ptr` into L1 (the epilogue warps read these lines a fraction of a coupling step later)
+    auto prefetch = [&](const void* ptr, int bytes) {
+      const char* c = reinterpret_cast<const char*>(ptr);
+      for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + o));
+    };
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
+      for (int c = a.c0; c < a.c1; ++c)
+        for (int k = 0; k < md.K; ++k) {
+          const StepDesc* sd = a.steps + (c * md.K + k);
+          prefetch(a.fblob + __ldg(&sd->ep_off), 6 * kEpPad * 4);
+          prefetch(a.iblob + __ldg(&sd->eidx_off), 2 * kEpPad * 4);
+          for (int net = 0; net < md.nnets; ++net) {
+            const int k0s = __ldg(&sd->layer[net][0].Kp) >> 4;
+            const int np3 = __ldg(&sd->layer[net][2].Np);
+            const __half* w1 = wb + __ldg(&sd->layer[net][0].w_off);
+            const __half* w2 = wb + __ldg(&sd->layer[net][1].w_off);
+            const __half* w3 = wb + __ldg(&sd->layer[net][2].w_off);
+            prefetch(a.fblob + __ldg(&sd->layer[net][0].b_off), md.h * 4);
+            prefetch(a.fblob + __ldg(&sd->layer[net][1].b_off), md.h * 4);
+            prefetch(a.fblob + __ldg(&sd->layer[net][2].b_off), np3 * 4);
+            const uint32_t l1_bytes = (uint32_t)k0s * 4096u, l3_bytes = (uint32_t)np3 * 128u;
+            for (int q = 0; q < NQ; ++q) push(w1 + (size_t)q * k0s * 2048, l1_bytes);
+            for (int q = 0; q < NQ; ++q) push(w2 + (size_t)(8 * q) * 1024, kTcStageBytes);
+            for (int j = 1; j < NJ; ++j) {
+              if (j >= 3) push(w3 + (size_t)(4 * (j - 3)) * np3 * 16, l3_bytes);
+              for (int q = 0; q < NQ; ++q) push(w2 + ((size_t)j * hs + 8 * q) * 1024, kTcStageBytes);
+            }
+            for (int j = (NJ > 3 ? NJ - 3 : 0); j < NJ; ++j) push(w3 + (size_t)(4 * j) * np3 * 16, l3_bytes);
+          }
+        }
+    if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) { a.prof[16] = T2_CLOCK() - p_t0; a.prof[17] = p_wait; a.prof[18] = sidx; }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================================
+    uint32_t units = 0;
+    uint32_t ph_sr = 0;                              // phase bits of the three hole barriers (bit i = parity of sr[i])
+    int nslot = 0;                                   // next ring slot / its parity, kept incrementally (no runtime % or /)
+    uint32_t npar = 0;
+    const long long m_t0 = T2_CLOCK();
+    long long m_wa = 0, m_wf = 0, m_iss = 0, m_sr = 0, tw, ti;
+    const uint64_t a0_desc = ptx::make_smem_desc(ptx::smem_u32(A0));
+    const uint64_t ring_desc = ptx::make_smem_desc(ptx::smem_u32(ring));
+    const uint32_t idesc_l1 = ptx::make_idesc_f16(128, kT2Chunk);
+    const uint32_t idesc_l2 = ptx::make_idesc_f16(128, kT2Piece);
+    int slot = 0;
+    // An mbarrier.try_wait costs 100-160 cycles on this warp even when the phase has long completed, and tcgen05.mma issue
+    // is nearly synchronous with execution (tools/tc_probe3.cu), so a wait placed between two MMA blocks idles the tensor
+    // pipe.  The readiness test of the NEXT stage is therefore issued before the current stage's MMAs and only consumed
+    // afterwards.
+    uint32_t full_ok = ptx::mbar_test_wait(&misc->full[0], 0u) ? 1u : 0u;
+    // wait for the next ring stage; returns its descriptor base
+    auto acquire = [&]() -> uint64_t {
+      slot = nslot;
+      tw = T2_CLOCK();
+      if (!full_ok) ptx::mbar_wait(&misc->full[slot], npar, a.error_flag, 21);
+      m_wf += T2_CLOCK() - tw;
+      ptx::tc_fence_after();
+      if (++nslot == nst) { nslot = 0; npar ^= 1u; }
+      full_ok = ptx::mbar_test_wait(&misc->full[nslot], npar) ? 1u : 0u;
+      return ring_desc + (uint64_t)((uint32_t)slot * (kTcStageBytes >> 4));
+    };
+    auto wait_epi = [&](uint64_t* bar, uint32_t par, int code) {
+      tw = T2_CLOCK();
+      t2_wait(bar, par, a.error_flag, code, lane);
+      m_wa += T2_CLOCK() - tw;
+      ptx::tc_fence_after();
+    };
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
+      for (int c = a.c0; c < a.c1; ++c)
+        for (int k = 0; k < md.K; ++k) {
+          const StepDesc* sd = a.steps + (c * md.K + k);
+          for (int net = 0; net < md.nnets; ++net, ++units) {
+            const int k0s = __ldg(&sd->layer[net][0].Kp) >> 4;
+            const int np3 = __ldg(&sd->layer[net][2].Np);
+            const uint32_t idesc_o = ptx::make_idesc_f16(128, np3);
+            const uint32_t b3_step = (uint32_t)np3 * 2u;       // (np3 * 32 B) >> 4
+            const uint32_t upar = units & 1u;
+            // layer-1 chunk q: A0 (smem) x W1 chunk -> T(q)
+            auto issue_l1 = [&](int q) {
+              const uint64_t bd = acquire();
+              ti = T2_CLOCK();
+              if (ptx::elect_one()) {
+                const uint32_t d = tbase + (uint32_t)q * kT2Chunk;
+                for (int i = 0; i < k0s; ++i)
+                  ptx::umma_f16(d, a0_desc + (uint64_t)(i * 256), bd + (uint64_t)(i * 256), idesc_l1, i > 0 ? 1u : 0u);
+                ptx::umma_commit(&misc->empty[slot]);
+                ptx::umma_commit(&misc->l1f[q]);
+              }
+              __syncwarp();
+              m_iss += T2_CLOCK() - ti;
+            };
+            // layer-2 chunk (hole hj), k-quarter q: A1 quarter q (TMEM T(q)[0:64]) x 8 k-slabs of [64 x 16]
+            auto issue_l2 = [&](int hj, int q) {
+              const uint64_t bd = acquire();
+              ti = T2_CLOCK();
+              if (ptx::elect_one()) {
+                const uint32_t d = tbase + t2_hole(hj);
+                const uint32_t at = tbase + (uint32_t)q * kT2Chunk;
+                ptx::umma_f16_ts(d, at, bd, idesc_l2, q > 0 ? 1u : 0u);
+#pragma unroll
+                for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bd + (uint64_t)(i * 128), idesc_l2, 1u);
+                ptx::umma_commit(&misc->empty[slot]);
+              }
+              __syncwarp();
+              m_iss += T2_CLOCK() - ti;
+            };
+            // last layer, k-piece j held in hole hj (packed pairs in its first 32 columns) -> H(3)
+            auto issue_l3 = [&](int j, int hj, uint32_t pre_ok) {
+              ti = T2_CLOCK();
+              if (!pre_ok) ptx::mbar_wait(&misc->sr[hj], (ph_sr >> hj) & 1u, a.error_flag, 23);
+              ptx::tc_fence_after();
+              m_sr += T2_CLOCK() - ti;
+              ph_sr ^= 1u << hj;
+              const uint64_t bd = acquire();
+              if (ptx::elect_one()) {
+                const uint32_t at = tbase + t2_hole(hj), d = tbase + t2_hole(3);
+                ptx::umma_f16_ts(d, at, bd, idesc_o, j > 0 ? 1u : 0u);
+                ptx::umma_f16_ts(d, at + 8u, bd + (uint64_t)b3_step, idesc_o, 1u);
+                ptx::umma_f16_ts(d, at + 16u, bd + (uint64_t)(2 * b3_step), idesc_o, 1u);
+                ptx::umma_f16_ts(d, at + 24u, bd + (uint64_t)(3 * b3_step), idesc_o, 1u);
+                ptx::umma_commit(&misc->empty[slot]);
+                if (j == NJ - 1) ptx::umma_commit(&misc->l3f);
+              }
+              __syncwarp();
+              T2_TRACE(20 + j);
+            };
+
+            wait_epi(&misc->a0r, upar, 20);
+            T2_TRACE(0);
+            for (int q = 0; q < NQ; ++q) { issue_l1(q); T2_TRACE(1 + q); }
+            for (int q = 0; q < NQ; ++q) {
+              wait_epi(&misc->a1r[q], upar, 22);
+              T2_TRACE(5 + q);
+              issue_l2(0, q);
+            }
+            if (ptx::elect_one()) ptx::umma_commit(&misc->l2f[0]);
+            __syncwarp();
+            T2_TRACE(10);
+            int hj = 1;
+            uint32_t sr_ok = 0;
+            for (int j = 1; j < NJ; ++j) {
+              if (j >= 3) issue_l3(j - 3, hj, sr_ok);       // frees hole hj (piece j - 3 lived there)
+              const int hn = (hj == 2) ? 0 : hj + 1;
+              // early readiness test of the piece the next iteration consumes (overlaps with this chunk's MMAs)
+              sr_ok = (j + 1 >= 3 && j + 1 < NJ) ? (ptx::mbar_test_wait(&misc->sr[hn], (ph_sr >> hn) & 1u) ? 1u : 0u) : 0u;
+              for (int q = 0; q < NQ; ++q) issue_l2(hj, q);
+              if (ptx::elect_one()) ptx::umma_commit(&misc->l2f[hj]);
+              __syncwarp();
+              T2_TRACE(10 + j);
+              hj = hn;
+            }
+            {
+              const int js = NJ > 3 ? NJ - 3 : 0;
+              int hl = js - 3 * (js / 3);
+              for (int j = js; j < NJ; ++j) { issue_l3(j, hl, 0u); hl = (hl == 2) ? 0 : hl + 1; }
+            }
+          }
+        }
+    if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) {
+      a.prof[0] = T2_CLOCK() - m_t0; a.prof[1] = m_wa; a.prof[2] = m_wf; a.prof[3] = units; a.prof[4] = m_iss; a.prof[5] = m_sr;
+    }
+  } else {
+    // ===================================== epilogue / elementwise warps =====================================
+    const int et = threadIdx.x - 64;
+    const int warp_e = et >> 5;
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int hsel = warp_e >> 2;          // which half of a chunk's columns
+    const int row = quad * 32 + lane;
+    float* zrow = zs + row * Dv;
+    const uint32_t lane_base = tbase + ((uint32_t)(quad * 32) << 16);
+    const int h0col = hsel == 0 ? 0 : (D + 1) / 2, h1col = hsel == 0 ? (D + 1) / 2 : D;   // column split for elementwise passes
+    uint32_t units = 0;
+    uint32_t ph_l2f = 0;
+    const long long e_t0 = T2_CLOCK();
+    long long e_w1 = 0, e_w2 = 0, e_w3 = 0, e_l1 = 0, e_l2 = 0, e_l3 = 0, e_pro = 0, e_x = 0, e_tmp;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const long long row0 = (long long)tile * kTcRows;
+      const long long gr = row0 + row;
+      OnlineLse lse; lse.init();
+      for (int c = a.c0; c < a.c1; ++c) {
+        // ---- x tile: fetched from HBM once per tile (8 independent loads in flight per thread) and kept in shared
+        //      memory; every component restarts from it ----
+        e_tmp = T2_CLOCK();
+        epi_bar();                                   // previous component's readers are done with zs / part
+        {
+          const int total = kTcRows * D;
+          if (c == a.c0) {
+            const long long gbase = row0 * D;
+            const long long glimit = a.B * (long long)D;
+            for (int i0 = et; i0 < total; i0 += 8 * kTcEpiThreads) {
+              float v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * kTcEpiThreads;
+                v[u] = (i < total && gbase + i < glimit) ? __ldg(a.x + gbase + i) : 0.f;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * kTcEpiThreads;
+                if (i < total) xs[i] = v[u];
+              }
+            }
+            epi_bar();
+          }
+          for (int i = et; i < total; i += kTcEpiThreads) { const int r = i / D; zs[r * Dv + (i - r * D)] = xs[i]; }
+          if (hsel == 0) for (int p = D; p < Dv; ++p) zrow[p] = 0.f;      // scratch column(s): target of padded table entries
+        }
+        epi_bar();
+        e_x += T2_CLOCK() - e_tmp;
+        float lsum = 0.f;                            // this thread's share of the data-dependent log-det
+        for (int k = 0; k < md.K; ++k) {
+          e_tmp = T2_CLOCK();
+          const StepDesc* sd = a.steps + (c * md.K + k);
+          const int out_dim = __ldg(&sd->out_dim), in_dim = __ldg(&sd->in_dim);
+          const float* tab = a.fblob + __ldg(&sd->ep_off);
+          const int* ix = a.iblob + __ldg(&sd->eidx_off);
+          // ---- ActNorm / eval-BatchNorm affine fused into the gather of z1 -> A0 (fp16, canonical layout, zero padded) ----
+          {
+            const int nch = __ldg(&sd->layer[0][0].Kp) >> 3;                // 8-element chunks
+            for (int ch = hsel; ch < nch; ch += 2) {
+              // loads first, stores last: the compiler cannot prove that the gathered columns are distinct, so an
+              // interleaved load / store sequence would be serialised on shared-memory latency
+              int col[8];
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) col[e] = __ldg(ix + ch * 8 + e);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = zrow[col[e]];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int j = ch * 8 + e;
+                v[e] = (v[e] + __ldg(tab + j)) * __ldg(tab + kEpPad + j) + __ldg(tab + 2 * kEpPad + j);
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) zrow[col[e]] = v[e];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = (ch * 8 + e < in_dim) ? v[e] : 0.f;
+              st_shared_v4(A0 + a_chunk_off(row, ch * 8), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                           pack_half2(v[6], v[7]));
+            }
+          }
+          e_pro += T2_CLOCK() - e_tmp;
+          for (int net = 0; net < md.nnets; ++net, ++units) {
+            const int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
+            const float* b1 = a.fblob + __ldg(&sd->layer[net][0].b_off);
+            const float* b2 = a.fblob + __ldg(&sd->layer[net][1].b_off);
+            const uint32_t upar = units & 1u;
+            const float* bias = a.fblob + __ldg(&sd->layer[net][2].b_off);
+            const int np3 = __ldg(&sd->layer[net][2].Np);
+            // hand A0 (and every drained TMEM region) to the MMA warp
+            ptx::fence_proxy_async_smem();
+            ptx::tc_fence_before();
+            t2_warp_arrive(&misc->a0r, lane);
+            if ((warp_e & 3) == 0) T2_TRACE(40 + 40 * hsel);
+            // ---- hidden layers.  The two epilogue warp groups (hsel) take ALTERNATE chunks and each thread owns a whole
+            //      row of its chunk, so one group's TMEM / barrier latencies hide behind the other group's MUFU work. ----
+            // layer 1: chunk q in T(q) (128 columns) -> act -> fp16 pairs packed in place into T(q)[0:64] (A1 k-quarter q);
+            // 32-column pieces, the next piece's tcgen05.ld in flight while this one is converted; the packed words of
+            // piece i land in columns [16 i, 16 i + 16), which this thread has already read.
+            for (int q = hsel; q < NQ; q += 2) {
+              e_tmp = T2_CLOCK();
+              t2_wait(&misc->l1f[q], upar, a.error_flag, 30, lane);
+              if ((warp_e & 3) == 0) T2_TRACE(41 + 40 * hsel + q);
+              e_w1 += T2_CLOCK() - e_tmp;
+              ptx::tc_fence_after();
+              e_tmp = T2_CLOCK();
+              const uint32_t tq = lane_base + (uint32_t)q * kT2Chunk;
+              const float* bq = b1 + q * kT2Chunk;
+              uint32_t ra[32], rb[32], p[16];
+              ptx::tmem_ld32(tq, ra);
+              ptx::tmem_ld_wait();
+              ptx::tmem_ld32(tq + 32u, rb);
+              if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(ra, bq, p); else t2_act_pack32<2, TANH_MODE>(ra, bq, p);
+              ptx::tmem_st16(tq, p);
+              ptx::tmem_ld_wait();
+              ptx::tmem_ld32(tq + 64u, ra);
+              if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(rb, bq + 32, p); else t2_act_pack32<2, TANH_MODE>(rb, bq + 32, p);
+              ptx::tmem_st16(tq + 16u, p);
+              ptx::tmem_ld_wait();
+              ptx::tmem_ld32(tq + 96u, rb);
+              if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(ra, bq + 64, p); else t2_act_pack32<2, TANH_MODE>(ra, bq + 64, p);
+              ptx::tmem_st16(tq + 32u, p);
+              ptx::tmem_ld_wait();
+              if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(rb, bq + 96, p); else t2_act_pack32<2, TANH_MODE>(rb, bq + 96, p);
+              ptx::tmem_st16(tq + 48u, p);
+              ptx::tmem_st_wait();
+              ptx::tc_fence_before();
+              t2_warp_arrive(&misc->a1r[q], lane);
+              if ((warp_e & 3) == 0) T2_TRACE(45 + 40 * hsel + q);
+              e_l1 += T2_CLOCK() - e_tmp;
+            }
+            // layer 2: 64-column chunk j in hole j mod 3 -> act -> packed in place into the hole's first 32 columns
+            // (k-piece j of the last layer's A operand).  Phase bits are advanced for EVERY chunk, also the other group's.
+            {
+              int hj = 0;
+              for (int j = 0; j < NJ; ++j) {
+                const uint32_t par = (ph_l2f >> hj) & 1u;
+                ph_l2f ^= 1u << hj;
+                if ((j & 1) == hsel) {
+                  e_tmp = T2_CLOCK();
+                  t2_wait(&misc->l2f[hj], par, a.error_flag, 31, lane);
+                  if ((warp_e & 3) == 0) T2_TRACE(50 + 40 * hsel + j);
+                  e_w2 += T2_CLOCK() - e_tmp;
+                  ptx::tc_fence_after();
+                  e_tmp = T2_CLOCK();
+                  const uint32_t th = lane_base + t2_hole(hj);
+                  const float* bj = b2 + j * kT2Piece;
+                  uint32_t ra[32], rb[32], p[16];
+                  ptx::tmem_ld32(th, ra);
+                  ptx::tmem_ld_wait();
+                  ptx::tmem_ld32(th + 32u, rb);
+                  if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(ra, bj, p); else t2_act_pack32<2, TANH_MODE>(ra, bj, p);
+                  ptx::tmem_st16(th, p);
+                  ptx::tmem_ld_wait();
+                  if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(rb, bj + 32, p); else t2_act_pack32<2, TANH_MODE>(rb, bj + 32, p);
+                  ptx::tmem_st16(th + 16u, p);
+                  ptx::tmem_st_wait();
+                  ptx::tc_fence_before();
+                  t2_warp_arrive(&misc->sr[hj], lane);
+                  if ((warp_e & 3) == 0) T2_TRACE(60 + 40 * hsel + j);
+                  e_l2 += T2_CLOCK() - e_tmp;
+                }
+                hj = (hj == 2) ? 0 : hj + 1;
+              }
+            }
+            // ---- last layer: coupling transform on this thread's 32-column slice of T(0)[0:64]; branch-free over the
+            //      padded gather-order tables (padded entries hit the scratch column and are masked out of the log-det) ----
+            e_tmp = T2_CLOCK();
+            t2_wait(&misc->l3f, upar, a.error_flag, 32, lane);
+            if ((warp_e & 3) == 0) T2_TRACE(70 + 40 * hsel);
+            e_w3 += T2_CLOCK() - e_tmp;
+            ptx::tc_fence_after();
+            e_tmp = T2_CLOCK();
+            const int c0 = hsel * 32;
+            if (c0 < np3) {
+              uint32_t r[32];
+              ptx::tmem_ld32(lane_base + t2_hole(3) + (uint32_t)c0, r);
+              ptx::tmem_ld_wait();
+              const float* add2 = tab + 3 * kEpPad;
+              const float* mul2 = tab + 4 * kEpPad;
+              const float* off2 = tab + 5 * kEpPad;
+              const int* ix2 = ix + kEpPad;
+              // every branch: gather the affected z2 columns first, store them last (see the gather above)
+              if (md.kind == GBNF_KIND_GLOW && md.coupling == GBNF_COUPLING_AFFINE) {
+                int col[16];
+                float z[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) col[jj] = __ldg(ix2 + hsel * 16 + jj);
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) z[jj] = zrow[col[jj]];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                  const int j = hsel * 16 + jj;
+                  const float shift = __uint_as_float(r[2 * jj]) + __ldg(bias + 2 * j);
+                  const float raw = __uint_as_float(r[2 * jj + 1]) + __ldg(bias + 2 * j + 1);
+                  const float s = __fdividef(1.0f, 1.0f + __expf(-(raw + 2.0f)));      // sigmoid(raw + 2), glow.py:333
+                  const float zn = (z[jj] + __ldg(add2 + j)) * __ldg(mul2 + j) + __ldg(off2 + j);
+                  z[jj] = (zn + shift) * s;                                             // glow.py:334-335
+                  lsum += (j < out_dim) ? __logf(s) : 0.f;                              // glow.py:338
+                }
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) zrow[col[jj]] = z[jj];
+              } else {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  if (c0 + half * 16 >= np3) break;
+                  int col[16];
+                  float z[16];
+#pragma unroll
+                  for (int jj = 0; jj < 16; ++jj) col[jj] = __ldg(ix2 + c0 + half * 16 + jj);
+#pragma unroll
+                  for (int jj = 0; jj < 16; ++jj) z[jj] = zrow[col[jj]];
+#pragma unroll
+                  for (int jj = 0; jj < 16; ++jj) {
+                    const int j = c0 + half * 16 + jj;
+                    const float acc = __uint_as_float(r[half * 16 + jj]) + __ldg(bias + j);
+                    const float zn = (z[jj] + __ldg(add2 + j)) * __ldg(mul2 + j) + __ldg(off2 + j);
+                    if (md.kind == GBNF_KIND_GLOW) {
+                      z[jj] = zn + acc;                                                 // additive coupling, glow.py:328-329
+                    } else if (net == 0) {                                              // RealNVP t_net: keep the shift
+                      if (j < out_dim) sh[row * plan.out_max + j] = acc;
+                    } else {                                                            // RealNVP s_net: transform
+                      const float t = (j < out_dim) ? sh[row * plan.out_max + j] : 0.f;
+                      z[jj] = t + zn * __expf(acc);                                     // transformations.py:575
+                      lsum += (j < out_dim) ? acc : 0.f;                                // transformations.py:577
+                    }
+                  }
+                  if (md.kind == GBNF_KIND_GLOW || net == 1) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) zrow[col[jj]] = z[jj];
+                  }
+                }
+              }
+            }
+            if (net == md.nnets - 1) t2_pair_bar(quad);   // z2 updates visible to the row's other thread before the next gather
+            if ((warp_e & 3) == 0) T2_TRACE(71 + 40 * hsel);
+            e_l3 += T2_CLOCK() - e_tmp;
+          }
+        }
+        // ---- component log-density for this row ----
+        const CompDesc& cd = a.comps[c];
+        const float* bm = a.fblob + cd.base_off;
+        const float* bi = bm + Dv;
+        float q = 0.f;
+        for (int p = h0col; p < h1col; ++p) { const float d = zrow[p] - __ldg(bm + p); q = fmaf(d * d, __ldg(bi + p), q); }
+        if (hsel == 1) { misc->part[row] = q; misc->part2[row] = lsum; }
+        t2_pair_bar(quad);
+        if (hsel == 0) {
+          q += misc->part[row];
+          const float ldj_tot = (lsum + misc->part2[row]) + __ldg(a.fblob + cd.const_off);
+          const float lq = (__ldg(bm + 2 * Dv) - q) + ldj_tot;
+          if (gr < a.B) {
+            if (a.logq) a.logq[gr * a.ld_logq + (c - a.c0)] = lq;
+            if (a.ldj_out) a.ldj_out[gr] = ldj_tot;
+          }
+          if (a.G_ll != nullptr && c < a.n_mix) lse.add(misc->coef[c] + lq);
+        }
+        if (a.z_out != nullptr && gr < a.B) {
+          const int* sig = a.iblob + cd.sigma_off;
+          for (int j = h0col; j < h1col; ++j) a.z_out[gr * D + j] = zrow[__ldg(sig + j)];
+        }
+      }
+      if (a.G_ll != nullptr && hsel == 0 && gr < a.B) a.G_ll[gr] = lse.value();
+    }
+    if (PROF && a.prof != nullptr && blockIdx.x == 0 && et == 0) {
+      a.prof[8] = T2_CLOCK() - e_t0; a.prof[9] = e_w1 + e_w2 + e_w3; a.prof[10] = e_l1 + e_l2; a.prof[11] = e_l3; a.prof[12] = e_pro + e_x;
+      a.prof[13] = e_w1; a.prof[14] = e_w2; a.prof[15] = e_w3; a.prof[19] = e_l1; a.prof[20] = e_l2; a.prof[21] = e_x; a.prof[22] = e_pro;
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tbase, 512);
+  }
+}
+
+#undef T2_CLOCK
+#undef T2_TRACE
+
+inline cudaError_t tc2_configure() {
+  cudaError_t e = cudaFuncSetAttribute(coupling_tc2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return e;
+}
+
+inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStream_t st, bool prof) {
+  if (prof) {
+    if (p.tanh_mode == 0) coupling_tc2_kernel<0, true><<<grid, kTcThreads, p.smem_bytes, st>>>(a, p);
+    else                  coupling_tc2_kernel<1, true><<<grid, kTcThreads, p.smem_bytes, st>>>(a, p);
+  } else {
+    if (p.tanh_mode == 0) coupling_tc2_kernel<0, false><<<grid, kTcThreads, p.smem_bytes, st>>>(a, p);
+    else                  coupling_tc2_kernel<1, false><<<grid, kTcThreads, p.smem_bytes, st>>>(a, p);
+  }
+  return 0;
+}
+
+}  // namespace gbnf

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -12,6 +13,7 @@
 #include "mixture.cuh"
 #include "coupling_fp32.cuh"
 #include "coupling_tc.cuh"
+#include "coupling_tc2.cuh"
 
 using namespace gbnf;
 
@@ -61,11 +63,13 @@ struct gbnf_ctx {
   double* tile_offs = nullptr;   // [cap_tiles + 1]
   long long cum_cap = 0;
   int* flags = nullptr;          // [0] kernel error flag, [1] fp16 overflow flag
-  long long* prof = nullptr;     // [32] cycle counters written by CTA 0 of the tensor-core kernel
+  long long* prof = nullptr;     // [32] cycle counters + [32..288) event trace written by CTA 0 of the tensor-core kernel
   // coupling launch plan
   int rows_per_cta = 0, ld = 0, out_max = 0, tmem_cols = 0;
   size_t smem_bytes = 0;
   TcPlan tc{};
+  bool tc2 = false;              // pipelined tensor-core kernel (coupling_tc2.cuh) selected
+  bool profiling = false;        // GBNF_PROF=1: launch the instrumented instantiation (gbnf_get_profile)
   int last_grid = 0;
   long long launches = 0;
 };
@@ -75,7 +79,8 @@ namespace {
 int plan_layout(gbnf_ctx* h) {
   const gbnf_config& c = h->cfg;
   ModelDims& md = h->md;
-  md.kind = c.kind; md.D = c.D; md.Dv = c.D | 1; md.h = c.h; md.K = c.K; md.C = c.C; md.depth = c.depth;
+  md.kind = c.kind; md.D = c.D; md.Dv = (c.D + 1) | 1;   // odd stride (bank-conflict free) with at least one scratch column at index D
+  md.h = c.h; md.K = c.K; md.C = c.C; md.depth = c.depth;
   md.act = c.act; md.coupling = c.coupling; md.base = c.base;
   md.nlayers = c.depth + 2;
   md.nnets = (c.kind == GBNF_KIND_REALNVP) ? 2 : 1;
@@ -96,6 +101,8 @@ int plan_layout(gbnf_ctx* h) {
       sd.has_affine = 0;   // filled at pack time (device does not read this copy); see pack
       sd.vec_off = f; f += round_up_ll(3LL * md.Dv, 4);
       sd.idx_off = i; i += round_up_ll(sd.in_dim + sd.out_dim, 4);
+      sd.ep_off = f; f += 6LL * kEpPad;
+      sd.eidx_off = i; i += 2LL * kEpPad;
       h->out_max = std::max(h->out_max, sd.out_dim);
       int n_last = sd.out_dim;
       if (c.kind == GBNF_KIND_GLOW && c.coupling == GBNF_COUPLING_AFFINE) n_last = 2 * sd.out_dim;
@@ -107,6 +114,7 @@ int plan_layout(gbnf_ctx* h) {
           L.Kp = round_up(L.K_in, kq);
           L.Np = round_up(L.N_out, nq);
           if (!f16 && l > 0) L.Kp = round_up(c.h, kF32KT);
+          L.NC = L.Np;
           L.w_off = w; w += (long long)L.Kp * L.Np;
           L.b_off = f; f += round_up_ll(L.Np, 4);
           if (l == 0) kp0_max = std::max(kp0_max, L.Kp);
@@ -131,9 +139,19 @@ int plan_layout(gbnf_ctx* h) {
     h->tmem_cols = 0;
     if (h->smem_bytes > 227 * 1024) return fail(GBNF_ERR_INVALID, "fp32 path: hidden width too large for shared memory");
   } else {
+    // pipelined kernel when the shape allows it (GBNF_TC_V1=1 forces the serial kernel, for A/B measurements)
+    const char* force_v1 = std::getenv("GBNF_TC_V1");
+    h->tc2 = tc2_eligible(md, h->steps_h) && !(force_v1 && force_v1[0] == '1');
     std::string why;
-    if (!tc_make_plan(md, h->steps_h, &h->tc, &why)) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: " + why);
+    if (h->tc2) {
+      if (!tc2_make_plan(md, h->steps_h, &h->tc)) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: shared memory budget exceeded");
+      for (StepDesc& sd : h->steps_h)
+        for (int net = 0; net < md.nnets; ++net) { sd.layer[net][0].NC = kT2Chunk; sd.layer[net][1].NC = kT2Piece; }
+    } else if (!tc_make_plan(md, h->steps_h, &h->tc, &why)) {
+      return fail(GBNF_ERR_INVALID, "f16 tensor-core path: " + why);
+    }
     h->tc.tanh_mode = (c.gemm_mode == GBNF_GEMM_F16_TC_FAST) ? 0 : 1;
+    { const char* pe = std::getenv("GBNF_PROF"); h->profiling = pe && pe[0] == '1'; }
     h->rows_per_cta = 128;
     h->smem_bytes = h->tc.smem_bytes;
     h->tmem_cols = h->tc.tmem_cols;
@@ -179,7 +197,7 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
     else if (R == 32) coupling_fp32_kernel<32><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
     else coupling_fp32_kernel<16><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
   } else {
-    int rc = tc_launch(a, h->tc, grid, st);
+    int rc = h->tc2 ? tc2_launch(a, h->tc, grid, st, h->profiling) : tc_launch(a, h->tc, grid, st);
     if (rc != 0) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: launch configuration rejected");
   }
   h->launches++;
@@ -242,8 +260,8 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   CREATE_TRY(cudaMalloc(&h->wsum, sizeof(double)));
   CREATE_TRY(cudaMalloc(&h->flags, 2 * sizeof(int)));
   CREATE_TRY(cudaMemset(h->flags, 0, 2 * sizeof(int)));
-  CREATE_TRY(cudaMalloc(&h->prof, 32 * sizeof(long long)));
-  CREATE_TRY(cudaMemset(h->prof, 0, 32 * sizeof(long long)));
+  CREATE_TRY(cudaMalloc(&h->prof, 288 * sizeof(long long)));
+  CREATE_TRY(cudaMemset(h->prof, 0, 288 * sizeof(long long)));
   CREATE_TRY(cudaMemcpy(h->comps_d, h->comps_h.data(), h->comps_h.size() * sizeof(CompDesc), cudaMemcpyHostToDevice));
   if (c.gemm_mode == GBNF_GEMM_FP32) {
     // the attribute is per FUNCTION, shared by all handles in the process: always raise it to the device maximum
@@ -253,6 +271,7 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
     CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   } else {
     CREATE_TRY(tc_configure(h->tc));
+    CREATE_TRY(tc2_configure());
   }
 #undef CREATE_TRY
   *out = h;
@@ -487,6 +506,13 @@ int gbnf_get_profile(gbnf_handle h, int64_t* out32) {
   return GBNF_OK;
 }
 
+int gbnf_get_trace(gbnf_handle h, int64_t* out256) {
+  if (!h || !out256) return fail(GBNF_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpy(out256, h->prof + 32, 256 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return GBNF_OK;
+}
+
 int gbnf_get_info(gbnf_handle h, gbnf_info* out) {
   if (!h || !out) return fail(GBNF_ERR_INVALID, "null argument");
   out->gemm_mode = h->cfg.gemm_mode;
@@ -497,6 +523,8 @@ int gbnf_get_info(gbnf_handle h, gbnf_info* out) {
   out->grid = h->last_grid;
   out->packed_bytes = h->w_bytes + h->f_count * 4 + h->i_count * 4;
   out->launches = h->launches;
+  out->pipelined = h->tc2 ? 1 : 0;
+  out->reserved = 0;
   return GBNF_OK;
 }
 

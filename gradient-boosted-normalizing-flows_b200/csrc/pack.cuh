@@ -70,6 +70,24 @@ __global__ void pack_meta_kernel(PackMetaArgs a) {
       }
     }
   }
+  // gather-order, padded copies of the step tables (pipelined tensor-core kernel)
+  for (int k = 0; k < a.md.K; ++k) {
+    const StepDesc& sd = a.sdesc[k];
+    const float* add = a.fblob + sd.vec_off;
+    const float* mul = add + Dv;
+    const float* off = mul + Dv;
+    const int* idx1 = a.iblob + sd.idx_off;
+    const int* idx2 = idx1 + sd.in_dim;
+    float* t = a.fblob + sd.ep_off;
+    int* ix = a.iblob + sd.eidx_off;
+    for (int j = 0; j < kEpPad; ++j) {
+      const bool v1 = j < sd.in_dim, v2 = j < sd.out_dim;
+      const int c1 = v1 ? idx1[j] : D, c2 = v2 ? idx2[j] : D;
+      ix[j] = c1; ix[kEpPad + j] = c2;
+      t[j] = v1 ? add[c1] : 0.f;               t[kEpPad + j] = v1 ? mul[c1] : 0.f;       t[2 * kEpPad + j] = v1 ? off[c1] : 0.f;
+      t[3 * kEpPad + j] = v2 ? add[c2] : 0.f;  t[4 * kEpPad + j] = v2 ? mul[c2] : 0.f;   t[5 * kEpPad + j] = v2 ? off[c2] : 0.f;
+    }
+  }
   int* sig_out = a.iblob + a.cdesc.sigma_off;
   for (int j = 0; j < D; ++j) sig_out[j] = sigma[j];
   a.fblob[a.cdesc.const_off] = (float)ldj_const;
@@ -111,11 +129,13 @@ __global__ void pack_weight_f16_kernel(const float* __restrict__ W, const float*
   const long long total = (long long)ld.Kp * ld.Np;
   __half* dst = wblob + ld.w_off;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    // decode destination index -> (n, k)
-    long long slab = i / ((long long)ld.Np * 16);
-    int r = (int)(i % ((long long)ld.Np * 16));
-    int grp = r / 128, kc = (r % 128) / 64, row = (r % 64) / 8, e = r % 8;
-    int n = grp * 8 + row, k = (int)slab * 16 + kc * 8 + e;
+    // decode destination index -> (n, k): [N chunk][k-slab][NC/8 row groups][2 k-chunks][8 rows][8 halves]
+    const int slab_elems = ld.NC * 16, nslabs = ld.Kp >> 4;
+    const long long cs = i / slab_elems;
+    const int chunk = (int)(cs / nslabs), slab = (int)(cs % nslabs);
+    const int r = (int)(i % slab_elems);
+    const int grp = r / 128, kc = (r % 128) / 64, row = (r % 64) / 8, e = r % 8;
+    const int n = chunk * ld.NC + grp * 8 + row, k = slab * 16 + kc * 8 + e;
     float v = (k < ld.K_in && n < ld.N_out) ? W[(long long)n * ld.K_in + k] : 0.f;
     __half hv = __float2half_rn(v);
     if (__hisinf(hv) || __hisnan(hv)) *overflow = 1;

@@ -170,6 +170,8 @@ typedef struct {
   int32_t grid;            /* CTAs launched by the last coupling launch */
   int64_t packed_bytes;    /* size of the packed parameter blob */
   int64_t launches;        /* kernels launched through this handle so far */
+  int32_t pipelined;       /* 1: chunk-pipelined tensor-core kernel (coupling_tc2.cuh), 0: serial / fp32 kernel */
+  int32_t reserved;
 } gbnf_info;
 int gbnf_get_info(gbnf_handle h, gbnf_info* out);
 
@@ -177,6 +179,10 @@ int gbnf_get_info(gbnf_handle h, gbnf_info* out);
  * [0..7] MMA warp: total, wait a_ready, wait weights, issue; [8..15] epilogue thread 0: total, wait accumulator,
  * hidden epilogues, last-layer/coupling, prologue (load/affine/gather); [16..] producer: total, wait empty. */
 int gbnf_get_profile(gbnf_handle h, int64_t* out32);
+
+/* Event trace (clock64 stamps) of one coupling pass of CTA 0 of the last pipelined tensor-core launch made with
+ * GBNF_PROF=1 in the environment; 256 entries, layout in tools/tc_trace.py (synchronises; diagnostics only). */
+int gbnf_get_trace(gbnf_handle h, int64_t* out256);
 
 #ifdef __cplusplus
 }

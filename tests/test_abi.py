@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Config) == 12 * 4
     assert C.sizeof(_lib.StepParams) == (7 + 2 * 2 * _lib.GBNF_MAX_LAYERS) * 8
     assert C.sizeof(_lib.ComponentParams) == 16
-    assert C.sizeof(_lib.Info) == 6 * 4 + 2 * 8
+    assert C.sizeof(_lib.Info) == 6 * 4 + 2 * 8 + 2 * 4
 
 
 def test_built_for_sm100a_with_lineinfo():

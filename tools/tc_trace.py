@@ -1,0 +1,46 @@
+"""Timeline (clock64 stamps, CTA 0, one coupling pass) of the pipelined tensor-core kernel.  Needs GBNF_PROF=1."""
+import os, sys
+os.environ["GBNF_PROF"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench, gbnf_b200
+
+cfg_name = sys.argv[1] if len(sys.argv) > 1 else "cfg3_miniboone"
+mode = sys.argv[2] if len(sys.argv) > 2 else "f16fast"
+cfg = bench.CONFIGS[cfg_name]
+dev = torch.device("cuda", 0)
+torch.manual_seed(1)
+model = gbnf_b200.BoostedFlow(bench.make_args(cfg, dev), gemm_mode=mode).to(dev)
+x = torch.randn((65536, cfg["D"]), device=dev)
+model.train()
+with torch.no_grad():
+    for c in range(cfg["C"]):
+        model(x=x[:4096], components=c)
+model.eval()
+for p in model.parameters():
+    p.requires_grad_(False)
+model.pack_all()
+for _ in range(2):
+    model.mixture_log_density(x, cfg["C"])
+torch.cuda.synchronize()
+t = model.trace()
+NQ, NJ = cfg["h"] // 128, cfg["h"] // 64
+names = {0: "MMA  a0r seen"}
+for q in range(NQ):
+    names[1 + q] = f"MMA  L1({q}) issued"; names[5 + q] = f"MMA  a1r[{q}] seen"
+for j in range(NJ):
+    names[10 + j] = f"MMA  L2 chunk {j} issued+committed"; names[20 + j] = f"MMA  L3({j}) issued"
+for g in (0, 1):
+    b = 40 + 40 * g
+    names[b] = f"EPI{g} a0r arrived (gather done)"
+    for q in range(NQ):
+        names[b + 1 + q] = f"EPI{g} l1f[{q}] seen"; names[b + 5 + q] = f"EPI{g} a1r[{q}] arrived (L1 chunk packed)"
+    for j in range(NJ):
+        names[b + 10 + j] = f"EPI{g} l2f chunk {j} seen"; names[b + 20 + j] = f"EPI{g} sr chunk {j} arrived"
+    names[b + 30] = f"EPI{g} l3f seen"; names[b + 31] = f"EPI{g} last-layer epilogue done"
+ev = sorted((v, names[i]) for i, v in enumerate(t) if v > 0 and i in names)
+t0 = ev[0][0]
+print(f"{cfg_name} {mode}: one coupling pass of CTA 0 (cycles relative to first event)")
+for v, n in ev:
+    print(f"{v - t0:8d}  {n}")
