@@ -359,14 +359,14 @@ def run_ours(a):
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=40)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--config", default="cfg3_miniboone", choices=list(CONFIGS))
-    p.add_argument("--mode", default=os.environ.get("GBNF_BENCH_MODE", "f16"), choices=["f16", "f16fast", "fp32"])
+    p.add_argument("--mode", default=os.environ.get("GBNF_BENCH_MODE", "f16fast"), choices=["f16", "f16fast", "fp32"])
     p.add_argument("--batch", type=int, default=65536)
     p.add_argument("--rows", type=int, default=1 << 20)
-    p.add_argument("--cpu-rows", type=int, default=131072)
+    p.add_argument("--cpu-rows", type=int, default=524288)
     p.add_argument("--no-cpu", action="store_true")
     a = p.parse_args()
     a.warmup = max(a.warmup, 3)

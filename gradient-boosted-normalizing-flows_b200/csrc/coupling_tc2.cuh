@@ -29,7 +29,10 @@ namespace gbnf {
 
 constexpr int kT2Chunk = 128;        // layer-1 chunk = k-quarter of layer 2
 constexpr int kT2Piece = 64;         // layer-2 chunk = k-piece of the last layer
-constexpr int kT2MaxStages = 12;
+constexpr int kT2Threads = 576;       // 2 control warps + 16 epilogue warps
+constexpr int kT2EpiThreads = 512;
+constexpr int kT2MaxStages = 8;
+constexpr uint32_t kT2StageBytes = 32768;   // ring slot: up to 16 layer-2 k-slabs; fewer, larger handshakes (see acquire())
 constexpr uint32_t kT2TraceUnit = 37;
 
 struct Tc2Misc {
@@ -44,8 +47,8 @@ struct Tc2Misc {
   uint32_t tmem_base;
   uint32_t pad_;
   float coef[kMaxComponents];
-  float part[kTcRows];
-  float part2[kTcRows];
+  float part[3 * kTcRows];
+  float part2[3 * kTcRows];
 };
 
 static_assert(sizeof(Tc2Misc) <= kTcMiscBytes, "misc region too small");
@@ -76,12 +79,14 @@ inline bool tc2_make_plan(const ModelDims& md, const std::vector<StepDesc>& step
   p->off_a1 = o;   o = al(o + kTcRows * md.D * 4);       // here: the untransformed x tile (reloaded into zs per component)
   p->off_sh = o;   o = al(o + (md.nnets == 2 ? kTcRows * out_max * 4 : 0));
   p->off_misc = o; o = al(o + kTcMiscBytes);
+  p->off_bias = o; o = al(o + (2 * md.h + 64) * 4);       // b1 | b2 | b3 of the current pass
+  p->off_tab = o;  o = al(o + 2 * 2 * kEpPad * 16);       // gather-order tables of the current and the next step
   p->off_ring = o;
   const uint32_t limit = 227 * 1024;
-  p->nst = std::min<int>(kT2MaxStages, (limit - o) / kTcStageBytes);
-  p->smem_bytes = o + (size_t)p->nst * kTcStageBytes;
+  p->nst = std::min<int>(kT2MaxStages, (limit - o) / kT2StageBytes);
+  p->smem_bytes = o + (size_t)p->nst * kT2StageBytes;
   p->tmem_cols = 512;
-  return p->nst >= 2;
+  return p->nst >= 4;
 }
 
 __device__ __forceinline__ uint32_t t2_hole(int i) { return 64u + 128u * (uint32_t)i; }
@@ -96,19 +101,77 @@ __device__ __forceinline__ void t2_wait(uint64_t* bar, uint32_t parity, int* err
   if (lane == 0) ptx::mbar_wait(bar, parity, err, code);
   __syncwarp();
 }
-// the two epilogue warps that share a TMEM lane quadrant (= the two threads of every row in it)
-__device__ __forceinline__ void t2_pair_bar(int quad) { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); }
+// the four epilogue warps that share a TMEM lane quadrant (= the four threads of every row in it)
+__device__ __forceinline__ void t2_quad_bar(int quad) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory"); }
+__device__ __forceinline__ void t2_epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
+// 16 accumulator values of one row -> bias + activation -> 8 packed fp16 pairs
+template <int ACT, int TANH_MODE>
+__device__ __forceinline__ void t2_act_pack16(const uint32_t (&r)[16], const float* __restrict__ bias, uint32_t* p) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);      // staged in shared memory (broadcast read)
+    p[2 * q + 0] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 0]) + b.x),
+                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 1]) + b.y));
+    p[2 * q + 1] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 2]) + b.z),
+                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 3]) + b.w));
+  }
+}
 // 32 accumulator values of one row -> bias + activation -> 16 packed fp16 pairs
 template <int ACT, int TANH_MODE>
 __device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const float* __restrict__ bias, uint32_t* p) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + 4 * q));
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
     p[2 * q + 0] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 0]) + b.x),
                               tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 1]) + b.y));
     p[2 * q + 1] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 2]) + b.z),
                               tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 3]) + b.w));
+  }
+}
+
+
+// ---- the fixed per-pass schedule, walked identically by the TMA producer and the MMA issuer ------------------------
+//   L1        (first chunk, #chunks)   ring stage: W1 chunks (as many as fit in a slot)
+//   WAIT_A1   (first quarter, #q)      MMA only : A1 k-quarters packed by the epilogue
+//   L2        (chunk j, k-half)        ring stage: the k-slabs of one k-half of layer-2 chunk j (<= 16 slabs, 32 KB)
+//   L2_DONE   (chunk j)                MMA only : commit -> epilogue
+//   L3_STAGE  (first piece, #pieces)   ring stage: last-layer k-slabs of 2 pieces.  The slot stays held while the two
+//                                      layer-2 stages between the pieces are consumed, which an in-order ring of >= 4
+//                                      slots tolerates (a 4-piece stage would deadlock a 5-slot ring)
+//   L3        (piece)                  MMA only : wait for the packed piece, accumulate it into H(3)
+// The first layer-2 chunks are accumulated k-half by k-half BEHIND the layer-1 epilogue, so the tensor pipe already works
+// while the MUFU-bound layer-1 activation is still running.
+enum { T2_OP_L1 = 0, T2_OP_WAIT_A1, T2_OP_L2, T2_OP_L2_DONE, T2_OP_L3_STAGE, T2_OP_L3 };
+template <class F>
+__device__ __forceinline__ void t2_schedule(int NQ, int NJ, int l1_per, F&& f) {
+  for (int q = 0; q < NQ; q += l1_per) f(T2_OP_L1, q, min(l1_per, NQ - q));
+  const int qh = (NQ + 1) >> 1, nhalf = NQ > 1 ? 2 : 1, NH = NJ < 3 ? NJ : 3;
+  // hole j (j < NQ) only becomes free when layer-1 chunk j has been packed, so behind the FIRST k-half of the layer-1
+  // epilogue only chunks j < qh may start
+  const int NS = nhalf == 2 ? (qh < NH ? qh : NH) : 0;
+  if (nhalf == 2) {
+    f(T2_OP_WAIT_A1, 0, qh);
+    for (int j = 0; j < NS; ++j) f(T2_OP_L2, j, 0);
+    f(T2_OP_WAIT_A1, qh, NQ - qh);
+    for (int j = 0; j < NS; ++j) { f(T2_OP_L2, j, 1); f(T2_OP_L2_DONE, j, 0); }
+  } else {
+    f(T2_OP_WAIT_A1, 0, NQ);
+  }
+  for (int j = NS; j < NH; ++j) {
+    for (int hf = 0; hf < nhalf; ++hf) f(T2_OP_L2, j, hf);
+    f(T2_OP_L2_DONE, j, 0);
+  }
+  for (int j = NH; j < NJ; ++j) {
+    const int pj = j - 3;
+    if ((pj & 1) == 0) f(T2_OP_L3_STAGE, pj, min(2, NJ - pj));
+    f(T2_OP_L3, pj, 0);
+    for (int hf = 0; hf < nhalf; ++hf) f(T2_OP_L2, j, hf);
+    f(T2_OP_L2_DONE, j, 0);
+  }
+  for (int pj = (NJ > 3 ? NJ - 3 : 0); pj < NJ; ++pj) {
+    if ((pj & 1) == 0) f(T2_OP_L3_STAGE, pj, min(2, NJ - pj));
+    f(T2_OP_L3, pj, 0);
   }
 }
 
@@ -118,14 +181,20 @@ __device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const flo
 // event trace of ONE coupling pass (unit kT2TraceUnit of CTA 0): a.prof[32 + id] = clock64(), see tools/tc_trace.py
 #define T2_TRACE(id) do { if (PROF && a.prof != nullptr && blockIdx.x == 0 && units == kT2TraceUnit && lane == 0) a.prof[32 + (id)] = clock64(); } while (0)
 template <int TANH_MODE, bool PROF>
-__global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArgs a, TcPlan plan) {
+__global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArgs a, TcPlan plan) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  // PTX predicate registers that carry the result of an early mbarrier.test_wait across the MMA block issued in between
+  // (warps issue in order: converting the predicate to a value right away would stall the issuer for the ~100-cycle
+  // latency of the test; see acquire() below)
+  asm volatile(".reg .pred t2_p_full;\n\t.reg .pred t2_p_sr;" ::);
   const ModelDims& md = a.md;
   const int D = md.D, Dv = md.Dv;
   float* zs = reinterpret_cast<float*>(smem + plan.off_zs);
   unsigned char* A0 = smem + plan.off_a0;
   float* xs = reinterpret_cast<float*>(smem + plan.off_a1);
   float* sh = reinterpret_cast<float*>(smem + plan.off_sh);
+  float* bias_s = reinterpret_cast<float*>(smem + plan.off_bias);
+  float4* tab_s = reinterpret_cast<float4*>(smem + plan.off_tab);
   Tc2Misc* misc = reinterpret_cast<Tc2Misc*>(smem + plan.off_misc);
   unsigned char* ring = smem + plan.off_ring;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,12 +202,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArg
   const int NQ = md.h / kT2Chunk;          // layer-1 chunks = k-quarters of layer 2
   const int NJ = md.h / kT2Piece;          // layer-2 chunks = k-pieces of the last layer
   const int hs = md.h >> 4;                // k-slabs of the h x h layer
+  const int qh = (NQ + 1) >> 1;            // k-quarters in the first k-half of layer 2
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nst; ++i) { ptx::mbar_init(&misc->full[i], 1); ptx::mbar_init(&misc->empty[i], 1); }
-    ptx::mbar_init(&misc->a0r, 8);
-    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&misc->a1r[i], 4); ptx::mbar_init(&misc->l1f[i], 1); }
-    for (int i = 0; i < 3; ++i) { ptx::mbar_init(&misc->sr[i], 4); ptx::mbar_init(&misc->l2f[i], 1); }
+    ptx::mbar_init(&misc->a0r, 16);
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&misc->a1r[i], 16); ptx::mbar_init(&misc->l1f[i], 1); }
+    for (int i = 0; i < 3; ++i) { ptx::mbar_init(&misc->sr[i], 16); ptx::mbar_init(&misc->l2f[i], 1); }
     ptx::mbar_init(&misc->l3f, 1);
     ptx::fence_mbar_init();
     if (a.G_ll != nullptr) mixture_coefficients(a.rho, a.n_mix, a.skip_c, a.mix_mode, misc->coef);
@@ -162,40 +232,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArg
       p_wait += T2_CLOCK() - tw;
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&misc->full[slot], bytes);
-        ptx::tma_bulk_g2s(ring + (size_t)slot * kTcStageBytes, src, bytes, &misc->full[slot]);
+        ptx::tma_bulk_g2s(ring + (size_t)slot * kT2StageBytes, src, bytes, &misc->full[slot]);
       }
       __syncwarp();
       ++sidx;
       if (++slot == nst) { slot = 0; par ^= 1u; }
     };
-    // pull `bytes` at `ptr` into L1 (the epilogue warps read these lines a fraction of a coupling step later)
-    auto prefetch = [&](const void* ptr, int bytes) {
-      const char* c = reinterpret_cast<const char*>(ptr);
-      for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + o));
-    };
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
       for (int c = a.c0; c < a.c1; ++c)
         for (int k = 0; k < md.K; ++k) {
           const StepDesc* sd = a.steps + (c * md.K + k);
-          prefetch(a.fblob + __ldg(&sd->ep_off), 6 * kEpPad * 4);
-          prefetch(a.iblob + __ldg(&sd->eidx_off), 2 * kEpPad * 4);
           for (int net = 0; net < md.nnets; ++net) {
             const int k0s = __ldg(&sd->layer[net][0].Kp) >> 4;
             const int np3 = __ldg(&sd->layer[net][2].Np);
             const __half* w1 = wb + __ldg(&sd->layer[net][0].w_off);
             const __half* w2 = wb + __ldg(&sd->layer[net][1].w_off);
             const __half* w3 = wb + __ldg(&sd->layer[net][2].w_off);
-            prefetch(a.fblob + __ldg(&sd->layer[net][0].b_off), md.h * 4);
-            prefetch(a.fblob + __ldg(&sd->layer[net][1].b_off), md.h * 4);
-            prefetch(a.fblob + __ldg(&sd->layer[net][2].b_off), np3 * 4);
-            const uint32_t l1_bytes = (uint32_t)k0s * 4096u, l3_bytes = (uint32_t)np3 * 128u;
-            for (int q = 0; q < NQ; ++q) push(w1 + (size_t)q * k0s * 2048, l1_bytes);
-            for (int q = 0; q < NQ; ++q) push(w2 + (size_t)(8 * q) * 1024, kTcStageBytes);
-            for (int j = 1; j < NJ; ++j) {
-              if (j >= 3) push(w3 + (size_t)(4 * (j - 3)) * np3 * 16, l3_bytes);
-              for (int q = 0; q < NQ; ++q) push(w2 + ((size_t)j * hs + 8 * q) * 1024, kTcStageBytes);
-            }
-            for (int j = (NJ > 3 ? NJ - 3 : 0); j < NJ; ++j) push(w3 + (size_t)(4 * j) * np3 * 16, l3_bytes);
+            const int l1_per = max(1, min(NQ, 8 / k0s));
+            t2_schedule(NQ, NJ, l1_per, [&](int op, int x, int y) {
+              if (op == T2_OP_L1) {
+                push(w1 + (size_t)x * k0s * 2048, (uint32_t)(y * k0s) * 4096u);
+              } else if (op == T2_OP_L2) {
+                const int qa = y ? qh : 0, nq = y ? NQ - qh : qh;
+                push(w2 + ((size_t)x * hs + 8 * qa) * 1024, (uint32_t)nq * 16384u);
+              } else if (op == T2_OP_L3_STAGE) {
+                push(w3 + (size_t)(4 * x) * np3 * 16, (uint32_t)(y * np3) * 128u);
+              }
+            });
           }
         }
     if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) { a.prof[16] = T2_CLOCK() - p_t0; a.prof[17] = p_wait; a.prof[18] = sidx; }
@@ -212,25 +275,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArg
     const uint32_t idesc_l1 = ptx::make_idesc_f16(128, kT2Chunk);
     const uint32_t idesc_l2 = ptx::make_idesc_f16(128, kT2Piece);
     int slot = 0;
-    // An mbarrier.try_wait costs 100-160 cycles on this warp even when the phase has long completed, and tcgen05.mma issue
-    // is nearly synchronous with execution (tools/tc_probe3.cu), so a wait placed between two MMA blocks idles the tensor
-    // pipe.  The readiness test of the NEXT stage is therefore issued before the current stage's MMAs and only consumed
-    // afterwards.
-    uint32_t full_ok = ptx::mbar_test_wait(&misc->full[0], 0u) ? 1u : 0u;
-    // wait for the next ring stage; returns its descriptor base
+    // An mbarrier test costs 100-160 cycles on this warp even when the phase has long completed, and tcgen05.mma issue is
+    // nearly synchronous with execution (tools/tc_probe3.cu, tc_probe4.cu): every handshake between two MMA blocks idles
+    // the tensor pipe.  Hence (1) ring slots are large (up to 16 MMAs per handshake) and (2) the readiness of the NEXT
+    // stage is tested (non-blocking) before the current stage's MMAs are issued and only consumed afterwards.
+    auto test_full = [&](uint64_t* bar, uint32_t par) {
+      asm volatile("mbarrier.test_wait.parity.shared::cta.b64 t2_p_full, [%0], %1;" ::"r"(ptx::smem_u32(bar)), "r"(par) : "memory");
+    };
+    test_full(&misc->full[0], 0u);
     auto acquire = [&]() -> uint64_t {
       slot = nslot;
       tw = T2_CLOCK();
+      uint32_t full_ok;
+      asm volatile("selp.u32 %0, 1, 0, t2_p_full;" : "=r"(full_ok));
       if (!full_ok) ptx::mbar_wait(&misc->full[slot], npar, a.error_flag, 21);
       m_wf += T2_CLOCK() - tw;
       ptx::tc_fence_after();
       if (++nslot == nst) { nslot = 0; npar ^= 1u; }
-      full_ok = ptx::mbar_test_wait(&misc->full[nslot], npar) ? 1u : 0u;
-      return ring_desc + (uint64_t)((uint32_t)slot * (kTcStageBytes >> 4));
+      test_full(&misc->full[nslot], npar);             // result consumed at the next acquire()
+      return ring_desc + (uint64_t)((uint32_t)slot * (kT2StageBytes >> 4));
     };
     auto wait_epi = [&](uint64_t* bar, uint32_t par, int code) {
       tw = T2_CLOCK();
-      t2_wait(bar, par, a.error_flag, code, lane);
+      ptx::mbar_wait(bar, par, a.error_flag, code);
       m_wa += T2_CLOCK() - tw;
       ptx::tc_fence_after();
     };
@@ -244,85 +311,96 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArg
             const uint32_t idesc_o = ptx::make_idesc_f16(128, np3);
             const uint32_t b3_step = (uint32_t)np3 * 2u;       // (np3 * 32 B) >> 4
             const uint32_t upar = units & 1u;
-            // layer-1 chunk q: A0 (smem) x W1 chunk -> T(q)
-            auto issue_l1 = [&](int q) {
-              const uint64_t bd = acquire();
-              ti = T2_CLOCK();
-              if (ptx::elect_one()) {
-                const uint32_t d = tbase + (uint32_t)q * kT2Chunk;
-                for (int i = 0; i < k0s; ++i)
-                  ptx::umma_f16(d, a0_desc + (uint64_t)(i * 256), bd + (uint64_t)(i * 256), idesc_l1, i > 0 ? 1u : 0u);
-                ptx::umma_commit(&misc->empty[slot]);
-                ptx::umma_commit(&misc->l1f[q]);
-              }
-              __syncwarp();
-              m_iss += T2_CLOCK() - ti;
-            };
-            // layer-2 chunk (hole hj), k-quarter q: A1 quarter q (TMEM T(q)[0:64]) x 8 k-slabs of [64 x 16]
-            auto issue_l2 = [&](int hj, int q) {
-              const uint64_t bd = acquire();
-              ti = T2_CLOCK();
-              if (ptx::elect_one()) {
-                const uint32_t d = tbase + t2_hole(hj);
-                const uint32_t at = tbase + (uint32_t)q * kT2Chunk;
-                ptx::umma_f16_ts(d, at, bd, idesc_l2, q > 0 ? 1u : 0u);
-#pragma unroll
-                for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bd + (uint64_t)(i * 128), idesc_l2, 1u);
-                ptx::umma_commit(&misc->empty[slot]);
-              }
-              __syncwarp();
-              m_iss += T2_CLOCK() - ti;
-            };
-            // last layer, k-piece j held in hole hj (packed pairs in its first 32 columns) -> H(3)
-            auto issue_l3 = [&](int j, int hj, uint32_t pre_ok) {
-              ti = T2_CLOCK();
-              if (!pre_ok) ptx::mbar_wait(&misc->sr[hj], (ph_sr >> hj) & 1u, a.error_flag, 23);
-              ptx::tc_fence_after();
-              m_sr += T2_CLOCK() - ti;
-              ph_sr ^= 1u << hj;
-              const uint64_t bd = acquire();
-              if (ptx::elect_one()) {
-                const uint32_t at = tbase + t2_hole(hj), d = tbase + t2_hole(3);
-                ptx::umma_f16_ts(d, at, bd, idesc_o, j > 0 ? 1u : 0u);
-                ptx::umma_f16_ts(d, at + 8u, bd + (uint64_t)b3_step, idesc_o, 1u);
-                ptx::umma_f16_ts(d, at + 16u, bd + (uint64_t)(2 * b3_step), idesc_o, 1u);
-                ptx::umma_f16_ts(d, at + 24u, bd + (uint64_t)(3 * b3_step), idesc_o, 1u);
-                ptx::umma_commit(&misc->empty[slot]);
-                if (j == NJ - 1) ptx::umma_commit(&misc->l3f);
-              }
-              __syncwarp();
-              T2_TRACE(20 + j);
-            };
+            const int l1_per = max(1, min(NQ, 8 / k0s));
+            uint64_t l3_desc = 0;                              // current last-layer stage: descriptor, slot, piece range
+            int l3_slot = 0, l3_first = 0, l3_last = -1;
+            uint32_t sr_pre = 0;                               // an early test of the next piece's barrier is pending in t2_p_sr
 
             wait_epi(&misc->a0r, upar, 20);
             T2_TRACE(0);
-            for (int q = 0; q < NQ; ++q) { issue_l1(q); T2_TRACE(1 + q); }
-            for (int q = 0; q < NQ; ++q) {
-              wait_epi(&misc->a1r[q], upar, 22);
-              T2_TRACE(5 + q);
-              issue_l2(0, q);
-            }
-            if (ptx::elect_one()) ptx::umma_commit(&misc->l2f[0]);
-            __syncwarp();
-            T2_TRACE(10);
-            int hj = 1;
-            uint32_t sr_ok = 0;
-            for (int j = 1; j < NJ; ++j) {
-              if (j >= 3) issue_l3(j - 3, hj, sr_ok);       // frees hole hj (piece j - 3 lived there)
-              const int hn = (hj == 2) ? 0 : hj + 1;
-              // early readiness test of the piece the next iteration consumes (overlaps with this chunk's MMAs)
-              sr_ok = (j + 1 >= 3 && j + 1 < NJ) ? (ptx::mbar_test_wait(&misc->sr[hn], (ph_sr >> hn) & 1u) ? 1u : 0u) : 0u;
-              for (int q = 0; q < NQ; ++q) issue_l2(hj, q);
-              if (ptx::elect_one()) ptx::umma_commit(&misc->l2f[hj]);
-              __syncwarp();
-              T2_TRACE(10 + j);
-              hj = hn;
-            }
-            {
-              const int js = NJ > 3 ? NJ - 3 : 0;
-              int hl = js - 3 * (js / 3);
-              for (int j = js; j < NJ; ++j) { issue_l3(j, hl, 0u); hl = (hl == 2) ? 0 : hl + 1; }
-            }
+            t2_schedule(NQ, NJ, l1_per, [&](int op, int x, int y) {
+              if (op == T2_OP_L1) {
+                // layer-1 chunks [x, x + y): A0 (smem) x W1 chunk -> T(q)
+                const uint64_t bd = acquire();
+                ti = T2_CLOCK();
+                if (ptx::elect_one()) {
+                  for (int q = x; q < x + y; ++q) {
+                    const uint32_t d = tbase + (uint32_t)q * kT2Chunk;
+                    const uint64_t bq = bd + (uint64_t)((q - x) * k0s * 256);
+                    for (int i = 0; i < k0s; ++i)
+                      ptx::umma_f16(d, a0_desc + (uint64_t)(i * 256), bq + (uint64_t)(i * 256), idesc_l1, i > 0 ? 1u : 0u);
+                    ptx::umma_commit(&misc->l1f[q]);
+                  }
+                  ptx::umma_commit(&misc->empty[slot]);
+                }
+                __syncwarp();
+                m_iss += T2_CLOCK() - ti;
+                T2_TRACE(1 + x);
+              } else if (op == T2_OP_WAIT_A1) {
+                for (int q = x; q < x + y; ++q) { wait_epi(&misc->a1r[q], upar, 22); T2_TRACE(5 + q); }
+              } else if (op == T2_OP_L2) {
+                // layer-2 chunk x (hole x mod 3), k-half y: A1 quarters from TMEM T(q)[0:64] x 8 k-slabs of [64 x 16] each
+                const int hj = x % 3;
+                const int qa = y ? qh : 0, nq = y ? NQ - qh : qh;
+                const bool last_half = (y == (NQ > 1 ? 1 : 0));
+                // early readiness test of the piece consumed right after this chunk (overlaps with the MMAs below)
+                if (last_half && x >= 2 && x + 1 < NJ) {
+                  const int hn = (x + 1) % 3;
+                  asm volatile("mbarrier.test_wait.parity.shared::cta.b64 t2_p_sr, [%0], %1;" ::"r"(ptx::smem_u32(&misc->sr[hn])),
+                               "r"((ph_sr >> hn) & 1u) : "memory");
+                  sr_pre = 1;
+                }
+                if (x == 4) T2_TRACE(130 + 3 * y);
+                const uint64_t bd = acquire();
+                if (x == 4) T2_TRACE(131 + 3 * y);
+                ti = T2_CLOCK();
+                if (ptx::elect_one()) {
+                  const uint32_t d = tbase + t2_hole(hj);
+                  for (int qq = 0; qq < nq; ++qq) {
+                    const uint32_t at = tbase + (uint32_t)(qa + qq) * kT2Chunk;
+                    const uint64_t bq = bd + (uint64_t)(qq * 1024);
+                    ptx::umma_f16_ts(d, at, bq, idesc_l2, (qa + qq) > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bq + (uint64_t)(i * 128), idesc_l2, 1u);
+                  }
+                  ptx::umma_commit(&misc->empty[slot]);
+                  if (last_half) ptx::umma_commit(&misc->l2f[hj]);     // chunk complete -> epilogue
+                }
+                __syncwarp();
+                m_iss += T2_CLOCK() - ti;
+                if (x == 4) T2_TRACE(132 + 3 * y);
+              } else if (op == T2_OP_L2_DONE) {
+                T2_TRACE(10 + x);
+              } else if (op == T2_OP_L3_STAGE) {
+                l3_desc = acquire();
+                l3_slot = slot; l3_first = x; l3_last = x + y - 1;
+              } else {
+                // last layer, k-piece x held in hole x mod 3 (k-slab i = 8 packed columns at hole + 16 i) -> H(3)
+                const int hj = x % 3;
+                if (x == 1) T2_TRACE(136);
+                ti = T2_CLOCK();
+                uint32_t sr_ok = 0;
+                if (sr_pre) asm volatile("selp.u32 %0, 1, 0, t2_p_sr;" : "=r"(sr_ok));
+                if (!sr_ok) ptx::mbar_wait(&misc->sr[hj], (ph_sr >> hj) & 1u, a.error_flag, 23);
+                ptx::tc_fence_after();
+                m_sr += T2_CLOCK() - ti;
+                ph_sr ^= 1u << hj;
+                sr_pre = 0;
+                if (x == 1) T2_TRACE(137);
+                if (ptx::elect_one()) {
+                  const uint32_t at = tbase + t2_hole(hj), d = tbase + t2_hole(3);
+                  const uint64_t bd = l3_desc + (uint64_t)((uint32_t)(x - l3_first) * 4u * b3_step);
+                  ptx::umma_f16_ts(d, at, bd, idesc_o, x > 0 ? 1u : 0u);
+                  ptx::umma_f16_ts(d, at + 16u, bd + (uint64_t)b3_step, idesc_o, 1u);
+                  ptx::umma_f16_ts(d, at + 32u, bd + (uint64_t)(2 * b3_step), idesc_o, 1u);
+                  ptx::umma_f16_ts(d, at + 48u, bd + (uint64_t)(3 * b3_step), idesc_o, 1u);
+                  if (x == l3_last) ptx::umma_commit(&misc->empty[l3_slot]);
+                  if (x == NJ - 1) ptx::umma_commit(&misc->l3f);
+                }
+                __syncwarp();
+                T2_TRACE(20 + x);
+              }
+            });
           }
         }
     if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) {
@@ -330,16 +408,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArg
     }
   } else {
     // ===================================== epilogue / elementwise warps =====================================
+    // 16 warps = 4 groups (g) x 4 TMEM lane quadrants: FOUR threads per row, each owning a quarter of every chunk's
+    // columns.  Four warps per scheduler hide the tcgen05.ld / st and barrier latencies of one another, which two
+    // warps per scheduler could not (measured: 27 % of the MUFU bound with 8 warps).
     const int et = threadIdx.x - 64;
     const int warp_e = et >> 5;
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
-    const int hsel = warp_e >> 2;          // which half of a chunk's columns
+    const int g = warp_e >> 2;             // column group 0..3
     const int row = quad * 32 + lane;
     float* zrow = zs + row * Dv;
     const uint32_t lane_base = tbase + ((uint32_t)(quad * 32) << 16);
-    const int h0col = hsel == 0 ? 0 : (D + 1) / 2, h1col = hsel == 0 ? (D + 1) / 2 : D;   // column split for elementwise passes
-    uint32_t units = 0;
+    const int dq = (D + 3) >> 2;
+    const int h0col = min(D, g * dq), h1col = min(D, (g + 1) * dq);   // column split for elementwise passes
+    uint32_t units = 0, stepc = 0;
     uint32_t ph_l2f = 0;
+    // the first step's gather-order tables; afterwards every step stages the tables of the one that follows it
+    if (blockIdx.x < a.num_tiles && et < 2 * kEpPad)
+      tab_s[et] = __ldg(reinterpret_cast<const float4*>(a.fblob + a.steps[a.c0 * md.K].ep_off) + et);
+    const bool tr = (warp_e & 3) == 0;     // one tracing warp per group
     const long long e_t0 = T2_CLOCK();
     long long e_w1 = 0, e_w2 = 0, e_w3 = 0, e_l1 = 0, e_l2 = 0, e_l3 = 0, e_pro = 0, e_x = 0, e_tmp;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -350,58 +436,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArg
         // ---- x tile: fetched from HBM once per tile (8 independent loads in flight per thread) and kept in shared
         //      memory; every component restarts from it ----
         e_tmp = T2_CLOCK();
-        epi_bar();                                   // previous component's readers are done with zs / part
+        t2_epi_bar();                                // previous component's readers are done with zs / part
         {
           const int total = kTcRows * D;
           if (c == a.c0) {
             const long long gbase = row0 * D;
             const long long glimit = a.B * (long long)D;
-            for (int i0 = et; i0 < total; i0 += 8 * kTcEpiThreads) {
+            for (int i0 = et; i0 < total; i0 += 8 * kT2EpiThreads) {
               float v[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * kTcEpiThreads;
+                const int i = i0 + u * kT2EpiThreads;
                 v[u] = (i < total && gbase + i < glimit) ? __ldg(a.x + gbase + i) : 0.f;
               }
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * kTcEpiThreads;
+                const int i = i0 + u * kT2EpiThreads;
                 if (i < total) xs[i] = v[u];
               }
             }
-            epi_bar();
+            t2_epi_bar();
           }
-          for (int i = et; i < total; i += kTcEpiThreads) { const int r = i / D; zs[r * Dv + (i - r * D)] = xs[i]; }
-          if (hsel == 0) for (int p = D; p < Dv; ++p) zrow[p] = 0.f;      // scratch column(s): target of padded table entries
+          for (int i = et; i < total; i += kT2EpiThreads) { const int r = i / D; zs[r * Dv + (i - r * D)] = xs[i]; }
+          if (g == 0) for (int p = D; p < Dv; ++p) zrow[p] = 0.f;         // scratch column(s): target of padded table entries
         }
-        epi_bar();
+        t2_epi_bar();
         e_x += T2_CLOCK() - e_tmp;
         float lsum = 0.f;                            // this thread's share of the data-dependent log-det
-        for (int k = 0; k < md.K; ++k) {
+        for (int k = 0; k < md.K; ++k, ++stepc) {
           e_tmp = T2_CLOCK();
           const StepDesc* sd = a.steps + (c * md.K + k);
           const int out_dim = __ldg(&sd->out_dim), in_dim = __ldg(&sd->in_dim);
-          const float* tab = a.fblob + __ldg(&sd->ep_off);
-          const int* ix = a.iblob + __ldg(&sd->eidx_off);
+          const float4* tab1 = tab_s + (stepc & 1u) * (2 * kEpPad);          // staged by the previous step
+          const float4* tab2 = tab1 + kEpPad;
+          // the step after this one (next k, next component, or the first step of this CTA's next tile)
+          const StepDesc* sd_next = (k + 1 < md.K) ? sd + 1
+                                    : (c + 1 < a.c1) ? a.steps + (c + 1) * md.K
+                                    : (tile + (int)gridDim.x < a.num_tiles) ? a.steps + a.c0 * md.K : nullptr;
           // ---- ActNorm / eval-BatchNorm affine fused into the gather of z1 -> A0 (fp16, canonical layout, zero padded) ----
           {
             const int nch = __ldg(&sd->layer[0][0].Kp) >> 3;                // 8-element chunks
-            for (int ch = hsel; ch < nch; ch += 2) {
+            for (int ch = g; ch < nch; ch += 4) {
               // loads first, stores last: the compiler cannot prove that the gathered columns are distinct, so an
               // interleaved load / store sequence would be serialised on shared-memory latency
-              int col[8];
+              float4 t[8];
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) col[e] = __ldg(ix + ch * 8 + e);
+              for (int e = 0; e < 8; ++e) t[e] = tab1[ch * 8 + e];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = zrow[col[e]];
+              for (int e = 0; e < 8; ++e) v[e] = zrow[__float_as_int(t[e].w)];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int j = ch * 8 + e;
-                v[e] = (v[e] + __ldg(tab + j)) * __ldg(tab + kEpPad + j) + __ldg(tab + 2 * kEpPad + j);
-              }
+              for (int e = 0; e < 8; ++e) v[e] = (v[e] + t[e].x) * t[e].y + t[e].z;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) zrow[col[e]] = v[e];
+              for (int e = 0; e < 8; ++e) zrow[__float_as_int(t[e].w)] = v[e];
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = (ch * 8 + e < in_dim) ? v[e] : 0.f;
               st_shared_v4(A0 + a_chunk_off(row, ch * 8), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
@@ -411,158 +498,161 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArg
           e_pro += T2_CLOCK() - e_tmp;
           for (int net = 0; net < md.nnets; ++net, ++units) {
             const int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
-            const float* b1 = a.fblob + __ldg(&sd->layer[net][0].b_off);
-            const float* b2 = a.fblob + __ldg(&sd->layer[net][1].b_off);
+            const float* b1 = bias_s + g * 32;
+            const float* b2 = bias_s + md.h + g * 16;
+            const float* bias = bias_s + 2 * md.h;
             const uint32_t upar = units & 1u;
-            const float* bias = a.fblob + __ldg(&sd->layer[net][2].b_off);
             const int np3 = __ldg(&sd->layer[net][2].Np);
             // hand A0 (and every drained TMEM region) to the MMA warp
             ptx::fence_proxy_async_smem();
             ptx::tc_fence_before();
             t2_warp_arrive(&misc->a0r, lane);
-            if ((warp_e & 3) == 0) T2_TRACE(40 + 40 * hsel);
-            // ---- hidden layers.  The two epilogue warp groups (hsel) take ALTERNATE chunks and each thread owns a whole
-            //      row of its chunk, so one group's TMEM / barrier latencies hide behind the other group's MUFU work. ----
-            // layer 1: chunk q in T(q) (128 columns) -> act -> fp16 pairs packed in place into T(q)[0:64] (A1 k-quarter q);
-            // 32-column pieces, the next piece's tcgen05.ld in flight while this one is converted; the packed words of
-            // piece i land in columns [16 i, 16 i + 16), which this thread has already read.
-            for (int q = hsel; q < NQ; q += 2) {
+            if (tr) T2_TRACE(40 + 40 * (g & 1));
+            // ---- stage this pass's biases (b1 | b2 | b3 are contiguous in fblob) and the next step's tables in shared
+            //      memory while the MMA warp issues layer 1: a first-touch global load in the chunk epilogues would stall
+            //      all four warps of a scheduler at once for an L2 round trip ----
+            t2_epi_bar();                              // nobody still reads the previous pass's biases
+            {
+              const float4* bsrc = reinterpret_cast<const float4*>(a.fblob + __ldg(&sd->layer[net][0].b_off));
+              const int nb4 = (2 * md.h + np3) >> 2;
+              for (int i = et; i < nb4; i += kT2EpiThreads) reinterpret_cast<float4*>(bias_s)[i] = __ldg(bsrc + i);
+              if (net == 0 && sd_next != nullptr && et >= kT2EpiThreads - 2 * kEpPad) {
+                const int i = et - (kT2EpiThreads - 2 * kEpPad);
+                tab_s[((stepc + 1) & 1u) * (2 * kEpPad) + i] = __ldg(reinterpret_cast<const float4*>(a.fblob + __ldg(&sd_next->ep_off)) + i);
+              }
+            }
+            t2_epi_bar();
+            // ---- layer 1: chunk q in T(q) (128 columns, 32 per thread) -> act -> fp16 pairs compacted into T(q)[0:64]
+            //      (A1 k-quarter q); the quadrant's four warps synchronise between reading and overwriting ----
+            for (int q = 0; q < NQ; ++q) {
               e_tmp = T2_CLOCK();
               t2_wait(&misc->l1f[q], upar, a.error_flag, 30, lane);
-              if ((warp_e & 3) == 0) T2_TRACE(41 + 40 * hsel + q);
+              if (tr) T2_TRACE(41 + 40 * (g & 1) + q);
               e_w1 += T2_CLOCK() - e_tmp;
               ptx::tc_fence_after();
               e_tmp = T2_CLOCK();
               const uint32_t tq = lane_base + (uint32_t)q * kT2Chunk;
-              const float* bq = b1 + q * kT2Chunk;
-              uint32_t ra[32], rb[32], p[16];
-              ptx::tmem_ld32(tq, ra);
-              ptx::tmem_ld_wait();
-              ptx::tmem_ld32(tq + 32u, rb);
-              if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(ra, bq, p); else t2_act_pack32<2, TANH_MODE>(ra, bq, p);
-              ptx::tmem_st16(tq, p);
-              ptx::tmem_ld_wait();
-              ptx::tmem_ld32(tq + 64u, ra);
-              if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(rb, bq + 32, p); else t2_act_pack32<2, TANH_MODE>(rb, bq + 32, p);
-              ptx::tmem_st16(tq + 16u, p);
-              ptx::tmem_ld_wait();
-              ptx::tmem_ld32(tq + 96u, rb);
-              if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(ra, bq + 64, p); else t2_act_pack32<2, TANH_MODE>(ra, bq + 64, p);
-              ptx::tmem_st16(tq + 32u, p);
-              ptx::tmem_ld_wait();
-              if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(rb, bq + 96, p); else t2_act_pack32<2, TANH_MODE>(rb, bq + 96, p);
-              ptx::tmem_st16(tq + 48u, p);
+              const bool fine = tr && g == 0 && q == 1;     // fine-grained stamps of one chunk epilogue (ids 120..)
+              if (fine) T2_TRACE(120);
+              uint32_t p[16];
+              {
+                uint32_t r[32];
+                ptx::tmem_ld32(tq + (uint32_t)g * 32u, r);
+                ptx::tmem_ld_wait();
+                if (fine) T2_TRACE(121);
+                if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, b1 + q * kT2Chunk, p);
+                else               t2_act_pack32<2, TANH_MODE>(r, b1 + q * kT2Chunk, p);
+              }
+              if (fine) T2_TRACE(122);
+              t2_quad_bar(quad);               // all four threads of the row have read their columns
+              if (fine) T2_TRACE(123);
+              ptx::tmem_st16(tq + (uint32_t)g * 16u, p);
               ptx::tmem_st_wait();
+              if (fine) T2_TRACE(124);
               ptx::tc_fence_before();
               t2_warp_arrive(&misc->a1r[q], lane);
-              if ((warp_e & 3) == 0) T2_TRACE(45 + 40 * hsel + q);
+              if (fine) T2_TRACE(125);
+              if (tr) T2_TRACE(45 + 40 * (g & 1) + q);
               e_l1 += T2_CLOCK() - e_tmp;
             }
-            // layer 2: 64-column chunk j in hole j mod 3 -> act -> packed in place into the hole's first 32 columns
-            // (k-piece j of the last layer's A operand).  Phase bits are advanced for EVERY chunk, also the other group's.
+            // ---- layer 2: 64-column chunk j in hole j mod 3 (16 columns per thread) -> act -> packed in place into the
+            //      first 8 of this thread's own columns = k-slab g of piece j of the last layer's A operand ----
             {
               int hj = 0;
               for (int j = 0; j < NJ; ++j) {
-                const uint32_t par = (ph_l2f >> hj) & 1u;
+                e_tmp = T2_CLOCK();
+                t2_wait(&misc->l2f[hj], (ph_l2f >> hj) & 1u, a.error_flag, 31, lane);
                 ph_l2f ^= 1u << hj;
-                if ((j & 1) == hsel) {
-                  e_tmp = T2_CLOCK();
-                  t2_wait(&misc->l2f[hj], par, a.error_flag, 31, lane);
-                  if ((warp_e & 3) == 0) T2_TRACE(50 + 40 * hsel + j);
-                  e_w2 += T2_CLOCK() - e_tmp;
-                  ptx::tc_fence_after();
-                  e_tmp = T2_CLOCK();
-                  const uint32_t th = lane_base + t2_hole(hj);
-                  const float* bj = b2 + j * kT2Piece;
-                  uint32_t ra[32], rb[32], p[16];
-                  ptx::tmem_ld32(th, ra);
+                if (tr) T2_TRACE(50 + 40 * (g & 1) + j);
+                e_w2 += T2_CLOCK() - e_tmp;
+                ptx::tc_fence_after();
+                e_tmp = T2_CLOCK();
+                const uint32_t th = lane_base + t2_hole(hj) + (uint32_t)g * 16u;
+                uint32_t p[8];
+                {
+                  uint32_t r[16];
+                  ptx::tmem_ld16(th, r);
                   ptx::tmem_ld_wait();
-                  ptx::tmem_ld32(th + 32u, rb);
-                  if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(ra, bj, p); else t2_act_pack32<2, TANH_MODE>(ra, bj, p);
-                  ptx::tmem_st16(th, p);
-                  ptx::tmem_ld_wait();
-                  if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(rb, bj + 32, p); else t2_act_pack32<2, TANH_MODE>(rb, bj + 32, p);
-                  ptx::tmem_st16(th + 16u, p);
-                  ptx::tmem_st_wait();
-                  ptx::tc_fence_before();
-                  t2_warp_arrive(&misc->sr[hj], lane);
-                  if ((warp_e & 3) == 0) T2_TRACE(60 + 40 * hsel + j);
-                  e_l2 += T2_CLOCK() - e_tmp;
+                  if (act_kind == 1) t2_act_pack16<1, TANH_MODE>(r, b2 + j * kT2Piece, p);
+                  else               t2_act_pack16<2, TANH_MODE>(r, b2 + j * kT2Piece, p);
                 }
+                ptx::tmem_st8(th, p);
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                t2_warp_arrive(&misc->sr[hj], lane);
+                if (tr) T2_TRACE(60 + 40 * (g & 1) + j);
                 hj = (hj == 2) ? 0 : hj + 1;
+                e_l2 += T2_CLOCK() - e_tmp;
               }
             }
-            // ---- last layer: coupling transform on this thread's 32-column slice of T(0)[0:64]; branch-free over the
-            //      padded gather-order tables (padded entries hit the scratch column and are masked out of the log-det) ----
+            // ---- last layer: coupling transform on this thread's 16-column slice of H(3); branch-free over the padded
+            //      gather-order tables (padded entries hit the scratch column and are masked out of the log-det) ----
             e_tmp = T2_CLOCK();
             t2_wait(&misc->l3f, upar, a.error_flag, 32, lane);
-            if ((warp_e & 3) == 0) T2_TRACE(70 + 40 * hsel);
+            if (tr) T2_TRACE(70 + 40 * (g & 1));
             e_w3 += T2_CLOCK() - e_tmp;
             ptx::tc_fence_after();
             e_tmp = T2_CLOCK();
-            const int c0 = hsel * 32;
+            const int c0 = g * 16;
             if (c0 < np3) {
-              uint32_t r[32];
-              ptx::tmem_ld32(lane_base + t2_hole(3) + (uint32_t)c0, r);
+              uint32_t r[16];
+              ptx::tmem_ld16(lane_base + t2_hole(3) + (uint32_t)c0, r);
               ptx::tmem_ld_wait();
-              const float* add2 = tab + 3 * kEpPad;
-              const float* mul2 = tab + 4 * kEpPad;
-              const float* off2 = tab + 5 * kEpPad;
-              const int* ix2 = ix + kEpPad;
               // every branch: gather the affected z2 columns first, store them last (see the gather above)
               if (md.kind == GBNF_KIND_GLOW && md.coupling == GBNF_COUPLING_AFFINE) {
-                int col[16];
-                float z[16];
+                const float2* bias2 = reinterpret_cast<const float2*>(bias);
+                float4 t[8];
+                float z[8];
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) col[jj] = __ldg(ix2 + hsel * 16 + jj);
+                for (int jj = 0; jj < 8; ++jj) t[jj] = tab2[g * 8 + jj];
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) z[jj] = zrow[col[jj]];
+                for (int jj = 0; jj < 8; ++jj) z[jj] = zrow[__float_as_int(t[jj].w)];
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                  const int j = hsel * 16 + jj;
-                  const float shift = __uint_as_float(r[2 * jj]) + __ldg(bias + 2 * j);
-                  const float raw = __uint_as_float(r[2 * jj + 1]) + __ldg(bias + 2 * j + 1);
+                for (int jj = 0; jj < 8; ++jj) {
+                  const int j = g * 8 + jj;
+                  const float2 b = bias2[j];
+                  const float shift = __uint_as_float(r[2 * jj]) + b.x;
+                  const float raw = __uint_as_float(r[2 * jj + 1]) + b.y;
                   const float s = __fdividef(1.0f, 1.0f + __expf(-(raw + 2.0f)));      // sigmoid(raw + 2), glow.py:333
-                  const float zn = (z[jj] + __ldg(add2 + j)) * __ldg(mul2 + j) + __ldg(off2 + j);
+                  const float zn = (z[jj] + t[jj].x) * t[jj].y + t[jj].z;
                   z[jj] = (zn + shift) * s;                                             // glow.py:334-335
                   lsum += (j < out_dim) ? __logf(s) : 0.f;                              // glow.py:338
                 }
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) zrow[col[jj]] = z[jj];
+                for (int jj = 0; jj < 8; ++jj) zrow[__float_as_int(t[jj].w)] = z[jj];
               } else {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                  if (c0 + half * 16 >= np3) break;
-                  int col[16];
-                  float z[16];
+                  float4 t[8];
+                  float z[8];
 #pragma unroll
-                  for (int jj = 0; jj < 16; ++jj) col[jj] = __ldg(ix2 + c0 + half * 16 + jj);
+                  for (int jj = 0; jj < 8; ++jj) t[jj] = tab2[c0 + half * 8 + jj];
 #pragma unroll
-                  for (int jj = 0; jj < 16; ++jj) z[jj] = zrow[col[jj]];
+                  for (int jj = 0; jj < 8; ++jj) z[jj] = zrow[__float_as_int(t[jj].w)];
 #pragma unroll
-                  for (int jj = 0; jj < 16; ++jj) {
-                    const int j = c0 + half * 16 + jj;
-                    const float acc = __uint_as_float(r[half * 16 + jj]) + __ldg(bias + j);
-                    const float zn = (z[jj] + __ldg(add2 + j)) * __ldg(mul2 + j) + __ldg(off2 + j);
+                  for (int jj = 0; jj < 8; ++jj) {
+                    const int j = c0 + half * 8 + jj;
+                    const float acc = __uint_as_float(r[half * 8 + jj]) + bias[j];
+                    const float zn = (z[jj] + t[jj].x) * t[jj].y + t[jj].z;
                     if (md.kind == GBNF_KIND_GLOW) {
                       z[jj] = zn + acc;                                                 // additive coupling, glow.py:328-329
                     } else if (net == 0) {                                              // RealNVP t_net: keep the shift
                       if (j < out_dim) sh[row * plan.out_max + j] = acc;
                     } else {                                                            // RealNVP s_net: transform
-                      const float t = (j < out_dim) ? sh[row * plan.out_max + j] : 0.f;
-                      z[jj] = t + zn * __expf(acc);                                     // transformations.py:575
+                      const float tt = (j < out_dim) ? sh[row * plan.out_max + j] : 0.f;
+                      z[jj] = tt + zn * __expf(acc);                                    // transformations.py:575
                       lsum += (j < out_dim) ? acc : 0.f;                                // transformations.py:577
                     }
                   }
                   if (md.kind == GBNF_KIND_GLOW || net == 1) {
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) zrow[col[jj]] = z[jj];
+                    for (int jj = 0; jj < 8; ++jj) zrow[__float_as_int(t[jj].w)] = z[jj];
                   }
                 }
               }
             }
-            if (net == md.nnets - 1) t2_pair_bar(quad);   // z2 updates visible to the row's other thread before the next gather
-            if ((warp_e & 3) == 0) T2_TRACE(71 + 40 * hsel);
+            if (net == md.nnets - 1) t2_quad_bar(quad);   // z2 updates visible to the row's other threads before the next gather
+            if (tr) T2_TRACE(71 + 40 * (g & 1));
             e_l3 += T2_CLOCK() - e_tmp;
           }
         }
@@ -572,11 +662,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArg
         const float* bi = bm + Dv;
         float q = 0.f;
         for (int p = h0col; p < h1col; ++p) { const float d = zrow[p] - __ldg(bm + p); q = fmaf(d * d, __ldg(bi + p), q); }
-        if (hsel == 1) { misc->part[row] = q; misc->part2[row] = lsum; }
-        t2_pair_bar(quad);
-        if (hsel == 0) {
-          q += misc->part[row];
-          const float ldj_tot = (lsum + misc->part2[row]) + __ldg(a.fblob + cd.const_off);
+        if (g > 0) { misc->part[(g - 1) * kTcRows + row] = q; misc->part2[(g - 1) * kTcRows + row] = lsum; }
+        t2_quad_bar(quad);
+        if (g == 0) {
+          q += misc->part[row] + misc->part[kTcRows + row] + misc->part[2 * kTcRows + row];
+          const float ldj_tot = (lsum + misc->part2[row] + misc->part2[kTcRows + row] + misc->part2[2 * kTcRows + row]) +
+                                __ldg(a.fblob + cd.const_off);
           const float lq = (__ldg(bm + 2 * Dv) - q) + ldj_tot;
           if (gr < a.B) {
             if (a.logq) a.logq[gr * a.ld_logq + (c - a.c0)] = lq;
@@ -589,7 +680,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc2_kernel(CouplingArg
           for (int j = h0col; j < h1col; ++j) a.z_out[gr * D + j] = zrow[__ldg(sig + j)];
         }
       }
-      if (a.G_ll != nullptr && hsel == 0 && gr < a.B) a.G_ll[gr] = lse.value();
+      if (a.G_ll != nullptr && g == 0 && gr < a.B) a.G_ll[gr] = lse.value();
     }
     if (PROF && a.prof != nullptr && blockIdx.x == 0 && et == 0) {
       a.prof[8] = T2_CLOCK() - e_t0; a.prof[9] = e_w1 + e_w2 + e_w3; a.prof[10] = e_l1 + e_l2; a.prof[11] = e_l3; a.prof[12] = e_pro + e_x;
@@ -618,11 +709,11 @@ inline cudaError_t tc2_configure() {
 
 inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStream_t st, bool prof) {
   if (prof) {
-    if (p.tanh_mode == 0) coupling_tc2_kernel<0, true><<<grid, kTcThreads, p.smem_bytes, st>>>(a, p);
-    else                  coupling_tc2_kernel<1, true><<<grid, kTcThreads, p.smem_bytes, st>>>(a, p);
+    if (p.tanh_mode == 0) coupling_tc2_kernel<0, true><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
+    else                  coupling_tc2_kernel<1, true><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
   } else {
-    if (p.tanh_mode == 0) coupling_tc2_kernel<0, false><<<grid, kTcThreads, p.smem_bytes, st>>>(a, p);
-    else                  coupling_tc2_kernel<1, false><<<grid, kTcThreads, p.smem_bytes, st>>>(a, p);
+    if (p.tanh_mode == 0) coupling_tc2_kernel<0, false><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
+    else                  coupling_tc2_kernel<1, false><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
   }
   return 0;
 }

@@ -101,8 +101,9 @@ int plan_layout(gbnf_ctx* h) {
       sd.has_affine = 0;   // filled at pack time (device does not read this copy); see pack
       sd.vec_off = f; f += round_up_ll(3LL * md.Dv, 4);
       sd.idx_off = i; i += round_up_ll(sd.in_dim + sd.out_dim, 4);
-      sd.ep_off = f; f += 6LL * kEpPad;
-      sd.eidx_off = i; i += 2LL * kEpPad;
+      f = round_up_ll(f, 4);
+      sd.ep_off = f; f += 8LL * kEpPad;
+      sd.eidx_off = 0;
       h->out_max = std::max(h->out_max, sd.out_dim);
       int n_last = sd.out_dim;
       if (c.kind == GBNF_KIND_GLOW && c.coupling == GBNF_COUPLING_AFFINE) n_last = 2 * sd.out_dim;

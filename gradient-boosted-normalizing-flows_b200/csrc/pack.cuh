@@ -78,14 +78,13 @@ __global__ void pack_meta_kernel(PackMetaArgs a) {
     const float* off = mul + Dv;
     const int* idx1 = a.iblob + sd.idx_off;
     const int* idx2 = idx1 + sd.in_dim;
-    float* t = a.fblob + sd.ep_off;
-    int* ix = a.iblob + sd.eidx_off;
+    float4* t1 = reinterpret_cast<float4*>(a.fblob + sd.ep_off);     // {add, mul, off, column (int bits)} in z1 order
+    float4* t2 = t1 + kEpPad;                                         // same in z2 order
     for (int j = 0; j < kEpPad; ++j) {
       const bool v1 = j < sd.in_dim, v2 = j < sd.out_dim;
       const int c1 = v1 ? idx1[j] : D, c2 = v2 ? idx2[j] : D;
-      ix[j] = c1; ix[kEpPad + j] = c2;
-      t[j] = v1 ? add[c1] : 0.f;               t[kEpPad + j] = v1 ? mul[c1] : 0.f;       t[2 * kEpPad + j] = v1 ? off[c1] : 0.f;
-      t[3 * kEpPad + j] = v2 ? add[c2] : 0.f;  t[4 * kEpPad + j] = v2 ? mul[c2] : 0.f;   t[5 * kEpPad + j] = v2 ? off[c2] : 0.f;
+      t1[j] = make_float4(v1 ? add[c1] : 0.f, v1 ? mul[c1] : 0.f, v1 ? off[c1] : 0.f, __int_as_float(c1));
+      t2[j] = make_float4(v2 ? add[c2] : 0.f, v2 ? mul[c2] : 0.f, v2 ? off[c2] : 0.f, __int_as_float(c2));
     }
   }
   int* sig_out = a.iblob + a.cdesc.sigma_off;

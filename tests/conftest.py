@@ -10,7 +10,8 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["glow_d43", "glow_d6_additive_relu", "realnvp_d6_bn", "realnvp_d5_mixed", "toy_d2"]
+GOLDEN_CASES = ["glow_d43", "glow_d6_additive_relu", "realnvp_d6_bn", "realnvp_d5_mixed", "glow_d43_h256", "realnvp_d6_h128_bn",
+                "toy_d2"]
 
 
 def pytest_configure(config):

@@ -7,5 +7,8 @@ CONFIGS = {
                                    flow_permutation="reverse"), 2, 160, False),
     "realnvp_d6_bn": (dict(kind="realnvp", D=6, C=4, K=5, h=64, batch_norm=True), 3, 200, False),
     "realnvp_d5_mixed": (dict(kind="realnvp", D=5, C=3, K=4, h=64, coupling_network="mixed"), 4, 130, False),
+    # wide enough (h % 128 == 0) for the pipelined tensor-core kernel: pins it against the reference itself
+    "glow_d43_h256": (dict(kind="glow", D=43, C=2, K=2, h=256), 6, 160, False),
+    "realnvp_d6_h128_bn": (dict(kind="realnvp", D=6, C=2, K=3, h=128, batch_norm=True), 7, 150, False),
     "toy_d2": (dict(kind="realnvp", D=2, C=8, K=1, h=64, rho_init="uniform"), 5, 100, True),
 }
