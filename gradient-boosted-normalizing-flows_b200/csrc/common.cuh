@@ -68,6 +68,12 @@ struct CouplingArgs {
   const void* wblob;
   ModelDims md;
   int num_tiles;
+  // pipelined kernel only: a row tile's components are split over `split` work units (better wave quantisation, more
+  // CTAs for small batches).  Every unit leaves its terms coef_c + log q_c in lse_terms; the last unit of a tile to
+  // arrive reduces them in component order, so G_ll does not depend on the split (nor on the batch size).
+  int split, comps_per_unit, num_units;
+  float* lse_terms;                // [num_tiles * 128][n_mix]
+  unsigned int* tile_ctr;          // [num_tiles], zero between launches (reset by the last arriver)
   int* error_flag;                 // device int, set non-zero on an internal timeout (f16 path)
   long long* prof;                 // optional cycle counters (CTA 0), see gbnf_get_profile
 };

@@ -45,7 +45,7 @@ struct Tc2Misc {
   uint64_t l2f[3];    // MMA -> epilogue : layer-2 chunk in hole i accumulated
   uint64_t l3f;       // MMA -> epilogue : last layer accumulated
   uint32_t tmem_base;
-  uint32_t pad_;
+  uint32_t last_flag;
   float coef[kMaxComponents];
   float part[3 * kTcRows];
   float part2[3 * kTcRows];
@@ -238,8 +238,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
       ++sidx;
       if (++slot == nst) { slot = 0; par ^= 1u; }
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
-      for (int c = a.c0; c < a.c1; ++c)
+    for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+      const int cb = a.c0 + (u % a.split) * a.comps_per_unit, ce = min(a.c1, cb + a.comps_per_unit);
+      for (int c = cb; c < ce; ++c)
         for (int k = 0; k < md.K; ++k) {
           const StepDesc* sd = a.steps + (c * md.K + k);
           for (int net = 0; net < md.nnets; ++net) {
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             });
           }
         }
+    }
     if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) { a.prof[16] = T2_CLOCK() - p_t0; a.prof[17] = p_wait; a.prof[18] = sidx; }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================================
@@ -301,8 +303,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
       m_wa += T2_CLOCK() - tw;
       ptx::tc_fence_after();
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
-      for (int c = a.c0; c < a.c1; ++c)
+    for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+      const int cb = a.c0 + (u % a.split) * a.comps_per_unit, ce = min(a.c1, cb + a.comps_per_unit);
+      for (int c = cb; c < ce; ++c)
         for (int k = 0; k < md.K; ++k) {
           const StepDesc* sd = a.steps + (c * md.K + k);
           for (int net = 0; net < md.nnets; ++net, ++units) {
@@ -403,6 +406,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             });
           }
         }
+    }
     if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) {
       a.prof[0] = T2_CLOCK() - m_t0; a.prof[1] = m_wa; a.prof[2] = m_wf; a.prof[3] = units; a.prof[4] = m_iss; a.prof[5] = m_sr;
     }
@@ -423,23 +427,26 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     uint32_t units = 0, stepc = 0;
     uint32_t ph_l2f = 0;
     // the first step's gather-order tables; afterwards every step stages the tables of the one that follows it
-    if (blockIdx.x < a.num_tiles && et < 2 * kEpPad)
-      tab_s[et] = __ldg(reinterpret_cast<const float4*>(a.fblob + a.steps[a.c0 * md.K].ep_off) + et);
+    if (blockIdx.x < a.num_units && et < 2 * kEpPad) {
+      const int cb0 = a.c0 + ((int)blockIdx.x % a.split) * a.comps_per_unit;
+      tab_s[et] = __ldg(reinterpret_cast<const float4*>(a.fblob + a.steps[cb0 * md.K].ep_off) + et);
+    }
     const bool tr = (warp_e & 3) == 0;     // one tracing warp per group
     const long long e_t0 = T2_CLOCK();
     long long e_w1 = 0, e_w2 = 0, e_w3 = 0, e_l1 = 0, e_l2 = 0, e_l3 = 0, e_pro = 0, e_x = 0, e_tmp;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+      const int tile = u / a.split, cs = u - tile * a.split;
+      const int cb = a.c0 + cs * a.comps_per_unit, ce = min(a.c1, cb + a.comps_per_unit);
       const long long row0 = (long long)tile * kTcRows;
       const long long gr = row0 + row;
-      OnlineLse lse; lse.init();
-      for (int c = a.c0; c < a.c1; ++c) {
+      for (int c = cb; c < ce; ++c) {
         // ---- x tile: fetched from HBM once per tile (8 independent loads in flight per thread) and kept in shared
         //      memory; every component restarts from it ----
         e_tmp = T2_CLOCK();
         t2_epi_bar();                                // previous component's readers are done with zs / part
         {
           const int total = kTcRows * D;
-          if (c == a.c0) {
+          if (c == cb) {
             const long long gbase = row0 * D;
             const long long glimit = a.B * (long long)D;
             for (int i0 = et; i0 < total; i0 += 8 * kT2EpiThreads) {
@@ -471,8 +478,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           const float4* tab2 = tab1 + kEpPad;
           // the step after this one (next k, next component, or the first step of this CTA's next tile)
           const StepDesc* sd_next = (k + 1 < md.K) ? sd + 1
-                                    : (c + 1 < a.c1) ? a.steps + (c + 1) * md.K
-                                    : (tile + (int)gridDim.x < a.num_tiles) ? a.steps + a.c0 * md.K : nullptr;
+                                    : (c + 1 < ce) ? a.steps + (c + 1) * md.K
+                                    : (u + (int)gridDim.x < a.num_units)
+                                        ? a.steps + (a.c0 + ((u + (int)gridDim.x) % a.split) * a.comps_per_unit) * md.K
+                                        : nullptr;
           // ---- ActNorm / eval-BatchNorm affine fused into the gather of z1 -> A0 (fp16, canonical layout, zero padded) ----
           {
             const int nch = __ldg(&sd->layer[0][0].Kp) >> 3;                // 8-element chunks
@@ -673,14 +682,35 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             if (a.logq) a.logq[gr * a.ld_logq + (c - a.c0)] = lq;
             if (a.ldj_out) a.ldj_out[gr] = ldj_tot;
           }
-          if (a.G_ll != nullptr && c < a.n_mix) lse.add(misc->coef[c] + lq);
+          if (a.G_ll != nullptr && c < a.n_mix) __stcg(a.lse_terms + ((long long)tile * kTcRows + row) * a.n_mix + c, misc->coef[c] + lq);
         }
         if (a.z_out != nullptr && gr < a.B) {
           const int* sig = a.iblob + cd.sigma_off;
           for (int j = h0col; j < h1col; ++j) a.z_out[gr * D + j] = zrow[__ldg(sig + j)];
         }
       }
-      if (a.G_ll != nullptr && g == 0 && gr < a.B) a.G_ll[gr] = lse.value();
+      if (a.G_ll != nullptr) {
+        // logsumexp over the tile's terms in component order (two passes: exact max, then the sum), by the last of the
+        // tile's `split` units to arrive
+        bool last = true;
+        if (a.split > 1) {
+          if (g == 0) __threadfence();
+          t2_epi_bar();
+          if (et == 0) misc->last_flag = (atomicAdd(a.tile_ctr + tile, 1u) == (unsigned)(a.split - 1)) ? 1u : 0u;
+          t2_epi_bar();
+          last = misc->last_flag != 0u;
+          if (last && et == 0) a.tile_ctr[tile] = 0u;
+          if (last && g == 0) __threadfence();
+        }
+        if (last && g == 0 && gr < a.B) {
+          const float* tv = a.lse_terms + ((long long)tile * kTcRows + row) * a.n_mix;
+          float M = -INFINITY;
+          for (int i = 0; i < a.n_mix; ++i) M = fmaxf(M, __ldcg(tv + i));
+          float S = 0.f;
+          for (int i = 0; i < a.n_mix; ++i) { const float t = __ldcg(tv + i); if (t != -INFINITY) S += expf(t - M); }
+          a.G_ll[gr] = (S > 0.f) ? M + logf(S) : 0.f;
+        }
+      }
     }
     if (PROF && a.prof != nullptr && blockIdx.x == 0 && et == 0) {
       a.prof[8] = T2_CLOCK() - e_t0; a.prof[9] = e_w1 + e_w2 + e_w3; a.prof[10] = e_l1 + e_l2; a.prof[11] = e_l3; a.prof[12] = e_pro + e_x;

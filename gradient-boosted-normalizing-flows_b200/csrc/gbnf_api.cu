@@ -63,6 +63,9 @@ struct gbnf_ctx {
   double* tile_offs = nullptr;   // [cap_tiles + 1]
   long long cum_cap = 0;
   int* flags = nullptr;          // [0] kernel error flag, [1] fp16 overflow flag
+  float* lse_part = nullptr;     // pipelined kernel: per-row mixture terms coef_c + log q_c (reduced by the last unit of a tile)
+  unsigned int* tile_ctr = nullptr;
+  long long lse_cap = 0, ctr_cap = 0;
   long long* prof = nullptr;     // [32] cycle counters + [32..288) event trace written by CTA 0 of the tensor-core kernel
   // coupling launch plan
   int rows_per_cta = 0, ld = 0, out_max = 0, tmem_cols = 0;
@@ -191,7 +194,38 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
   a.prof = h->prof;
   const int R = h->rows_per_cta;
   a.num_tiles = (int)((B + R - 1) / R);
-  const int grid = std::min(a.num_tiles, h->num_sms);
+  a.split = 1; a.comps_per_unit = c1 - c0; a.num_units = a.num_tiles;
+  if (h->cfg.gemm_mode != GBNF_GEMM_FP32 && h->tc2) {
+    // split every tile's components over S units when that shortens the critical CTA (waves x components per unit)
+    const int ncomp = c1 - c0;
+    long long best = -1;
+    for (int S = 1; S <= ncomp; S *= 2) {
+      const int cpu = (ncomp + S - 1) / S;
+      const int units = a.num_tiles * ((ncomp + cpu - 1) / cpu);
+      const long long cost = (long long)((units + h->num_sms - 1) / h->num_sms) * cpu;
+      if (best < 0 || cost < best) { best = cost; a.comps_per_unit = cpu; a.split = (ncomp + cpu - 1) / cpu; }
+    }
+    a.num_units = a.num_tiles * a.split;
+    if (G_ll != nullptr) {
+      const long long need = (long long)a.num_tiles * R * std::max(1, n_mix);
+      if (need > h->lse_cap) {
+        if (h->lse_part) cudaFree(h->lse_part);
+        h->lse_part = nullptr; h->lse_cap = 0;
+        CUDA_TRY(cudaMalloc(&h->lse_part, need * sizeof(float)));
+        h->lse_cap = need;
+      }
+      if (a.num_tiles > h->ctr_cap) {
+        if (h->tile_ctr) cudaFree(h->tile_ctr);
+        h->tile_ctr = nullptr; h->ctr_cap = 0;
+        const long long cap = std::max<long long>(a.num_tiles, 1024);
+        CUDA_TRY(cudaMalloc(&h->tile_ctr, cap * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemsetAsync(h->tile_ctr, 0, cap * sizeof(unsigned int), st));
+        h->ctr_cap = cap;
+      }
+      a.lse_terms = h->lse_part; a.tile_ctr = h->tile_ctr;
+    }
+  }
+  const int grid = std::min(a.num_units, h->num_sms);
   h->last_grid = grid;
   if (h->cfg.gemm_mode == GBNF_GEMM_FP32) {
     if (R == 64) coupling_fp32_kernel<64><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
@@ -284,6 +318,7 @@ void gbnf_destroy(gbnf_handle h) {
   cudaSetDevice(h->cfg.device);
   cudaFree(h->steps_d); cudaFree(h->comps_d); cudaFree(h->fblob); cudaFree(h->iblob); cudaFree(h->wblob);
   cudaFree(h->step_params_d); cudaFree(h->partial); cudaFree(h->ticket); cudaFree(h->ms); cudaFree(h->wsum);
+  cudaFree(h->lse_part); cudaFree(h->tile_ctr);
   cudaFree(h->cum); cudaFree(h->tile_sums); cudaFree(h->tile_offs); cudaFree(h->flags); cudaFree(h->prof);
   delete h;
 }
