@@ -74,6 +74,7 @@ struct CouplingArgs {
   int split, comps_per_unit, num_units;
   float* lse_terms;                // [num_tiles * 128][n_mix]
   unsigned int* tile_ctr;          // [num_tiles], zero between launches (reset by the last arriver)
+  int exp_flags;                   // experiments (GBNF_EXP env, diagnostics only): bit 0 = producer skips the weight copies
   int* error_flag;                 // device int, set non-zero on an internal timeout (f16 path)
   long long* prof;                 // optional cycle counters (CTA 0), see gbnf_get_profile
 };

@@ -177,10 +177,10 @@ __device__ __forceinline__ void t2_schedule(int NQ, int NJ, int l1_per, F&& f) {
 
 // PROF: per-role cycle counters of CTA 0 (gbnf_get_profile).  A clock64() costs ~30 cycles on the latency-bound single-warp
 // roles, so the counters are compiled out of the production instantiation.
-#define T2_CLOCK() (PROF ? clock64() : 0LL)
+#define T2_CLOCK() (PROF == 1 ? clock64() : 0LL)
 // event trace of ONE coupling pass (unit kT2TraceUnit of CTA 0): a.prof[32 + id] = clock64(), see tools/tc_trace.py
 #define T2_TRACE(id) do { if (PROF && a.prof != nullptr && blockIdx.x == 0 && units == kT2TraceUnit && lane == 0) a.prof[32 + (id)] = clock64(); } while (0)
-template <int TANH_MODE, bool PROF>
+template <int TANH_MODE, int PROF>   // PROF: 0 production, 1 cycle counters + event trace, 2 event trace only (near-production timing)
 __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArgs a, TcPlan plan) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // PTX predicate registers that carry the result of an early mbarrier.test_wait across the MMA block issued in between
@@ -231,8 +231,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
       t2_wait(&misc->empty[slot], par ^ 1u, a.error_flag, 10, lane);
       p_wait += T2_CLOCK() - tw;
       if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(&misc->full[slot], bytes);
-        ptx::tma_bulk_g2s(ring + (size_t)slot * kT2StageBytes, src, bytes, &misc->full[slot]);
+        if (a.exp_flags & 1) {
+          ptx::mbar_arrive(&misc->full[slot]);          // timing experiment: no data movement (results are garbage)
+        } else {
+          ptx::mbar_arrive_expect_tx(&misc->full[slot], bytes);
+          ptx::tma_bulk_g2s(ring + (size_t)slot * kT2StageBytes, src, bytes, &misc->full[slot]);
+        }
       }
       __syncwarp();
       ++sidx;
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           }
         }
     }
-    if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) { a.prof[16] = T2_CLOCK() - p_t0; a.prof[17] = p_wait; a.prof[18] = sidx; }
+    if (PROF == 1 && a.prof != nullptr && blockIdx.x == 0 && lane == 0) { a.prof[16] = T2_CLOCK() - p_t0; a.prof[17] = p_wait; a.prof[18] = sidx; }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================================
     uint32_t units = 0;
@@ -297,6 +301,22 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
       test_full(&misc->full[nslot], npar);             // result consumed at the next acquire()
       return ring_desc + (uint64_t)((uint32_t)slot * (kT2StageBytes >> 4));
     };
+    // The tensor pipe queues only ~5 MMAs (~160 cycles of N=64 work), so the bookkeeping of acquire() is hidden only when
+    // it runs while MMAs are still queued: an op takes the NEXT ring stage before it issues its own last four MMAs.
+    uint64_t pre_desc = 0;
+    int pre_slot = 0;
+    bool pre_valid = false;
+    auto stage_take = [&]() -> uint64_t {
+      if (pre_valid) { pre_valid = false; slot = pre_slot; return pre_desc; }
+      return acquire();
+    };
+    auto stage_prefetch = [&]() {
+      const int keep = slot;
+      pre_desc = acquire();
+      pre_slot = slot;
+      pre_valid = true;
+      slot = keep;
+    };
     auto wait_epi = [&](uint64_t* bar, uint32_t par, int code) {
       tw = T2_CLOCK();
       ptx::mbar_wait(bar, par, a.error_flag, code);
@@ -324,7 +344,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             t2_schedule(NQ, NJ, l1_per, [&](int op, int x, int y) {
               if (op == T2_OP_L1) {
                 // layer-1 chunks [x, x + y): A0 (smem) x W1 chunk -> T(q)
-                const uint64_t bd = acquire();
+                const uint64_t bd = stage_take();
                 ti = T2_CLOCK();
                 if (ptx::elect_one()) {
                   for (int q = x; q < x + y; ++q) {
@@ -354,19 +374,37 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                   sr_pre = 1;
                 }
                 if (x == 4) T2_TRACE(130 + 3 * y);
-                const uint64_t bd = acquire();
+                const uint64_t bd = stage_take();
+                const int cur_slot = slot;
                 if (x == 4) T2_TRACE(131 + 3 * y);
                 ti = T2_CLOCK();
+                const uint32_t d = tbase + t2_hole(hj);
                 if (ptx::elect_one()) {
-                  const uint32_t d = tbase + t2_hole(hj);
                   for (int qq = 0; qq < nq; ++qq) {
                     const uint32_t at = tbase + (uint32_t)(qa + qq) * kT2Chunk;
                     const uint64_t bq = bd + (uint64_t)(qq * 1024);
                     ptx::umma_f16_ts(d, at, bq, idesc_l2, (qa + qq) > 0 ? 1u : 0u);
-#pragma unroll
-                    for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bq + (uint64_t)(i * 128), idesc_l2, 1u);
+                    ptx::umma_f16_ts(d, at + 8u, bq + 128u, idesc_l2, 1u);
+                    ptx::umma_f16_ts(d, at + 16u, bq + 256u, idesc_l2, 1u);
+                    ptx::umma_f16_ts(d, at + 24u, bq + 384u, idesc_l2, 1u);
+                    if (qq < nq - 1) {
+                      ptx::umma_f16_ts(d, at + 32u, bq + 512u, idesc_l2, 1u);
+                      ptx::umma_f16_ts(d, at + 40u, bq + 640u, idesc_l2, 1u);
+                      ptx::umma_f16_ts(d, at + 48u, bq + 768u, idesc_l2, 1u);
+                      ptx::umma_f16_ts(d, at + 56u, bq + 896u, idesc_l2, 1u);
+                    }
                   }
-                  ptx::umma_commit(&misc->empty[slot]);
+                }
+                __syncwarp();
+                stage_prefetch();                                      // a later stage always exists after a layer-2 op
+                if (ptx::elect_one()) {
+                  const uint32_t at = tbase + (uint32_t)(qa + nq - 1) * kT2Chunk + 32u;
+                  const uint64_t bq = bd + (uint64_t)((nq - 1) * 1024 + 512);
+                  ptx::umma_f16_ts(d, at, bq, idesc_l2, 1u);
+                  ptx::umma_f16_ts(d, at + 8u, bq + 128u, idesc_l2, 1u);
+                  ptx::umma_f16_ts(d, at + 16u, bq + 256u, idesc_l2, 1u);
+                  ptx::umma_f16_ts(d, at + 24u, bq + 384u, idesc_l2, 1u);
+                  ptx::umma_commit(&misc->empty[cur_slot]);
                   if (last_half) ptx::umma_commit(&misc->l2f[hj]);     // chunk complete -> epilogue
                 }
                 __syncwarp();
@@ -375,7 +413,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               } else if (op == T2_OP_L2_DONE) {
                 T2_TRACE(10 + x);
               } else if (op == T2_OP_L3_STAGE) {
-                l3_desc = acquire();
+                l3_desc = stage_take();
                 l3_slot = slot; l3_first = x; l3_last = x + y - 1;
               } else {
                 // last layer, k-piece x held in hole x mod 3 (k-slab i = 8 packed columns at hole + 16 i) -> H(3)
@@ -407,7 +445,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           }
         }
     }
-    if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) {
+    if (PROF == 1 && a.prof != nullptr && blockIdx.x == 0 && lane == 0) {
       a.prof[0] = T2_CLOCK() - m_t0; a.prof[1] = m_wa; a.prof[2] = m_wf; a.prof[3] = units; a.prof[4] = m_iss; a.prof[5] = m_sr;
     }
   } else {
@@ -712,7 +750,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
         }
       }
     }
-    if (PROF && a.prof != nullptr && blockIdx.x == 0 && et == 0) {
+    if (PROF == 1 && a.prof != nullptr && blockIdx.x == 0 && et == 0) {
       a.prof[8] = T2_CLOCK() - e_t0; a.prof[9] = e_w1 + e_w2 + e_w3; a.prof[10] = e_l1 + e_l2; a.prof[11] = e_l3; a.prof[12] = e_pro + e_x;
       a.prof[13] = e_w1; a.prof[14] = e_w2; a.prof[15] = e_w3; a.prof[19] = e_l1; a.prof[20] = e_l2; a.prof[21] = e_x; a.prof[22] = e_pro;
     }
@@ -730,21 +768,20 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
 #undef T2_TRACE
 
 inline cudaError_t tc2_configure() {
-  cudaError_t e = cudaFuncSetAttribute(coupling_tc2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(coupling_tc2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   return e;
 }
 
-inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStream_t st, bool prof) {
-  if (prof) {
-    if (p.tanh_mode == 0) coupling_tc2_kernel<0, true><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
-    else                  coupling_tc2_kernel<1, true><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
-  } else {
-    if (p.tanh_mode == 0) coupling_tc2_kernel<0, false><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
-    else                  coupling_tc2_kernel<1, false><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
-  }
+inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStream_t st, int prof) {
+#define T2_GO(T, P) coupling_tc2_kernel<T, P><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p)
+  if (p.tanh_mode == 0) { if (prof == 1) T2_GO(0, 1); else if (prof == 2) T2_GO(0, 2); else T2_GO(0, 0); }
+  else                  { if (prof == 1) T2_GO(1, 1); else if (prof == 2) T2_GO(1, 2); else T2_GO(1, 0); }
+#undef T2_GO
   return 0;
 }
 

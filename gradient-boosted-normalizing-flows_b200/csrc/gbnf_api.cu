@@ -72,7 +72,7 @@ struct gbnf_ctx {
   size_t smem_bytes = 0;
   TcPlan tc{};
   bool tc2 = false;              // pipelined tensor-core kernel (coupling_tc2.cuh) selected
-  bool profiling = false;        // GBNF_PROF=1: launch the instrumented instantiation (gbnf_get_profile)
+  int profiling = 0;             // GBNF_PROF=1: cycle counters + event trace, 2: event trace only (gbnf_get_profile / _trace)
   int last_grid = 0;
   long long launches = 0;
 };
@@ -155,7 +155,7 @@ int plan_layout(gbnf_ctx* h) {
       return fail(GBNF_ERR_INVALID, "f16 tensor-core path: " + why);
     }
     h->tc.tanh_mode = (c.gemm_mode == GBNF_GEMM_F16_TC_FAST) ? 0 : 1;
-    { const char* pe = std::getenv("GBNF_PROF"); h->profiling = pe && pe[0] == '1'; }
+    { const char* pe = std::getenv("GBNF_PROF"); h->profiling = (pe && pe[0] >= '1' && pe[0] <= '2') ? pe[0] - '0' : 0; }
     h->rows_per_cta = 128;
     h->smem_bytes = h->tc.smem_bytes;
     h->tmem_cols = h->tc.tmem_cols;
@@ -191,6 +191,7 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
   a.rho = rho; a.n_mix = n_mix; a.skip_c = skip_c; a.mix_mode = mix_mode; a.G_ll = G_ll;
   a.steps = h->steps_d; a.comps = h->comps_d; a.fblob = h->fblob; a.iblob = h->iblob; a.wblob = h->wblob; a.md = h->md;
   a.error_flag = h->flags;
+  { const char* ee = std::getenv("GBNF_EXP"); a.exp_flags = ee ? std::atoi(ee) : 0; }
   a.prof = h->prof;
   const int R = h->rows_per_cta;
   a.num_tiles = (int)((B + R - 1) / R);

@@ -1,6 +1,6 @@
 """Timeline (clock64 stamps, CTA 0, one coupling pass) of the pipelined tensor-core kernel.  Needs GBNF_PROF=1."""
 import os, sys
-os.environ["GBNF_PROF"] = "1"
+os.environ.setdefault("GBNF_PROF", "2")   # 2: event trace only (near-production timing), 1: plus cycle counters
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
@@ -21,7 +21,7 @@ model.eval()
 for p in model.parameters():
     p.requires_grad_(False)
 model.pack_all()
-for _ in range(2):
+for _ in range(30):   # let the clocks ramp up; the trace of the last launch is read
     model.mixture_log_density(x, cfg["C"])
 torch.cuda.synchronize()
 t = model.trace()
