@@ -21,7 +21,8 @@ constexpr int kEpPad = 64;             // padded length of the gather-order step
 //               [Np/NC chunks][Kp/16 k-slabs][NC x 16] with the same canonical layout inside each NC x 16 slab.
 struct LayerDesc {
   int K_in, N_out, Kp, Np;
-  int NC, pad_;      // N-chunk width of the f16 image (== Np for the single-chunk layout)
+  int NC, NC2;       // N-chunk width of the f16 image (== Np for the single-chunk layout); NC2 != 0: width of the odd
+                     // chunks (chunk widths alternate NC, NC2, NC, ...: h = 512 in the pipelined kernel uses 128 / 64)
   long long w_off;   // element offset into wblob (float for fp32, __half for f16)
   long long b_off;   // float offset into fblob; Np entries, zero padded
 };

@@ -58,7 +58,7 @@ inline bool tc2_eligible(const ModelDims& md, const std::vector<StepDesc>& steps
   if (md.nlayers != 3 || md.h % kT2Chunk != 0 || md.h > 512 || md.D > kTcMaxD) return false;
   for (const StepDesc& s : steps)
     for (int n = 0; n < md.nnets; ++n) {
-      if (s.layer[n][0].Kp > 64) return false;          // one ring stage holds the k-slabs of a layer-1 chunk
+      if (s.layer[n][0].Kp > 32) return false;          // one ring stage holds W1 of all (<= 4) layer-1 chunks
       if (s.layer[n][2].Np > 64) return false;          // last-layer accumulator is the 64-column hole H(3)
     }
   return true;
@@ -131,48 +131,50 @@ __device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const flo
 }
 
 
+// ---- TMEM geometry ---------------------------------------------------------------------------------------------
+// A1 (layer-2 A operand, fp16 pairs) occupies columns [0, h/2): k-quarter q at [64 q, 64 q + 64).  Two accumulator slots
+// follow; layer-2 chunk j lives in slot j & 1, layer-1 chunk q in L1 slot q & 1 (always 128 wide).  h = 512 leaves only
+// 256 columns: slot 0 = 128, slot 1 = 64, last-layer accumulator = 64, and layer 2 is cut into chunks of 128/64/128/64/128
+// columns; narrower models use two 128-column slots.  128-column accumulators matter because a tcgen05.mma costs ~44 cycles
+// to issue (blocking issue + descriptor arithmetic) but an N=64 MMA executes in 32: only N=128 keeps the pipe busy.
+struct T2Geom {
+  int NQ, NJ;
+  bool tight;
+  uint32_t slot_col[2], l1_col[2], la_col;
+  __device__ __forceinline__ int cw(int j) const { return (tight && (j & 1)) ? 64 : 128; }
+  __device__ __forceinline__ int ccol(int j) const { return tight ? 192 * (j >> 1) + ((j & 1) ? 128 : 0) : 128 * j; }
+};
+__device__ __forceinline__ T2Geom t2_geom(int h) {
+  T2Geom g;
+  g.NQ = h / kT2Chunk;
+  g.tight = (h == 512);
+  g.NJ = g.tight ? 5 : g.NQ;
+  const uint32_t a1w = (uint32_t)h >> 1;
+  g.slot_col[0] = a1w; g.slot_col[1] = a1w + 128u;
+  g.l1_col[0] = a1w;   g.l1_col[1] = a1w + 128u;
+  g.la_col = g.tight ? 448u : a1w + 256u;
+  return g;
+}
+
 // ---- the fixed per-pass schedule, walked identically by the TMA producer and the MMA issuer ------------------------
-//   L1        (first chunk, #chunks)   ring stage: W1 chunks (as many as fit in a slot)
-//   WAIT_A1   (first quarter, #q)      MMA only : A1 k-quarters packed by the epilogue
-//   L2        (chunk j, k-half)        ring stage: the k-slabs of one k-half of layer-2 chunk j (<= 16 slabs, 32 KB)
-//   L2_DONE   (chunk j)                MMA only : commit -> epilogue
-//   L3_STAGE  (first piece, #pieces)   ring stage: last-layer k-slabs of 2 pieces.  The slot stays held while the two
-//                                      layer-2 stages between the pieces are consumed, which an in-order ring of >= 4
-//                                      slots tolerates (a 4-piece stage would deadlock a 5-slot ring)
-//   L3        (piece)                  MMA only : wait for the packed piece, accumulate it into H(3)
-// The first layer-2 chunks are accumulated k-half by k-half BEHIND the layer-1 epilogue, so the tensor pipe already works
-// while the MUFU-bound layer-1 activation is still running.
-enum { T2_OP_L1 = 0, T2_OP_WAIT_A1, T2_OP_L2, T2_OP_L2_DONE, T2_OP_L3_STAGE, T2_OP_L3 };
+//   L1_STAGE  ()                 ring stage: W1 of all layer-1 chunks (held while the chunks are issued)
+//   L1        (chunk q)          MMA only  : A0 x W1 chunk q -> L1 slot q & 1 (chunks >= 2 wait for the slot to be drained)
+//   L2        (chunk j, part p)  ring stage: 32 KB of chunk j's weights = one k-quarter of a 128-column chunk, or two
+//                                            k-quarters of a 64-column chunk; needs A1 quarters and a free slot
+//   L2_DONE   (chunk j)          MMA only  : commit -> epilogue
+//   L3        (piece j)          ring stage: last-layer k-slabs of piece j; waits for the packed piece, accumulates it
+enum { T2_OP_L1_STAGE = 0, T2_OP_L1, T2_OP_L2, T2_OP_L2_DONE, T2_OP_L3 };
 template <class F>
-__device__ __forceinline__ void t2_schedule(int NQ, int NJ, int l1_per, F&& f) {
-  for (int q = 0; q < NQ; q += l1_per) f(T2_OP_L1, q, min(l1_per, NQ - q));
-  const int qh = (NQ + 1) >> 1, nhalf = NQ > 1 ? 2 : 1, NH = NJ < 3 ? NJ : 3;
-  // hole j (j < NQ) only becomes free when layer-1 chunk j has been packed, so behind the FIRST k-half of the layer-1
-  // epilogue only chunks j < qh may start
-  const int NS = nhalf == 2 ? (qh < NH ? qh : NH) : 0;
-  if (nhalf == 2) {
-    f(T2_OP_WAIT_A1, 0, qh);
-    for (int j = 0; j < NS; ++j) f(T2_OP_L2, j, 0);
-    f(T2_OP_WAIT_A1, qh, NQ - qh);
-    for (int j = 0; j < NS; ++j) { f(T2_OP_L2, j, 1); f(T2_OP_L2_DONE, j, 0); }
-  } else {
-    f(T2_OP_WAIT_A1, 0, NQ);
-  }
-  for (int j = NS; j < NH; ++j) {
-    for (int hf = 0; hf < nhalf; ++hf) f(T2_OP_L2, j, hf);
+__device__ __forceinline__ void t2_schedule(const T2Geom& g, F&& f) {
+  f(T2_OP_L1_STAGE, 0, 0);
+  for (int q = 0; q < g.NQ; ++q) f(T2_OP_L1, q, 0);
+  for (int j = 0; j < g.NJ; ++j) {
+    if (j >= 2) f(T2_OP_L3, j - 2, 0);                       // frees slot j & 1
+    const int parts = (g.cw(j) == 128) ? g.NQ : (g.NQ + 1) / 2;
+    for (int p = 0; p < parts; ++p) f(T2_OP_L2, j, p);
     f(T2_OP_L2_DONE, j, 0);
   }
-  for (int j = NH; j < NJ; ++j) {
-    const int pj = j - 3;
-    if ((pj & 1) == 0) f(T2_OP_L3_STAGE, pj, min(2, NJ - pj));
-    f(T2_OP_L3, pj, 0);
-    for (int hf = 0; hf < nhalf; ++hf) f(T2_OP_L2, j, hf);
-    f(T2_OP_L2_DONE, j, 0);
-  }
-  for (int pj = (NJ > 3 ? NJ - 3 : 0); pj < NJ; ++pj) {
-    if ((pj & 1) == 0) f(T2_OP_L3_STAGE, pj, min(2, NJ - pj));
-    f(T2_OP_L3, pj, 0);
-  }
+  for (int j = (g.NJ >= 2 ? g.NJ - 2 : 0); j < g.NJ; ++j) f(T2_OP_L3, j, 0);
 }
 
 // PROF: per-role cycle counters of CTA 0 (gbnf_get_profile).  A clock64() costs ~30 cycles on the latency-bound single-warp
@@ -199,10 +201,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
   unsigned char* ring = smem + plan.off_ring;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nst = plan.nst;
-  const int NQ = md.h / kT2Chunk;          // layer-1 chunks = k-quarters of layer 2
-  const int NJ = md.h / kT2Piece;          // layer-2 chunks = k-pieces of the last layer
+  const T2Geom G = t2_geom(md.h);
+  const int NQ = G.NQ;                     // layer-1 chunks = k-quarters of layer 2
+  const int NJ = G.NJ;                     // layer-2 chunks = k-pieces of the last layer
   const int hs = md.h >> 4;                // k-slabs of the h x h layer
-  const int qh = (NQ + 1) >> 1;            // k-quarters in the first k-half of layer 2
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nst; ++i) { ptx::mbar_init(&misc->full[i], 1); ptx::mbar_init(&misc->empty[i], 1); }
@@ -253,15 +255,19 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             const __half* w1 = wb + __ldg(&sd->layer[net][0].w_off);
             const __half* w2 = wb + __ldg(&sd->layer[net][1].w_off);
             const __half* w3 = wb + __ldg(&sd->layer[net][2].w_off);
-            const int l1_per = max(1, min(NQ, 8 / k0s));
-            t2_schedule(NQ, NJ, l1_per, [&](int op, int x, int y) {
-              if (op == T2_OP_L1) {
-                push(w1 + (size_t)x * k0s * 2048, (uint32_t)(y * k0s) * 4096u);
+            t2_schedule(G, [&](int op, int x, int y) {
+              if (op == T2_OP_L1_STAGE) {
+                push(w1, (uint32_t)(NQ * k0s) * 4096u);
               } else if (op == T2_OP_L2) {
-                const int qa = y ? qh : 0, nq = y ? NQ - qh : qh;
-                push(w2 + ((size_t)x * hs + 8 * qa) * 1024, (uint32_t)nq * 16384u);
-              } else if (op == T2_OP_L3_STAGE) {
-                push(w3 + (size_t)(4 * x) * np3 * 16, (uint32_t)(y * np3) * 128u);
+                const __half* base = w2 + (size_t)G.ccol(x) * hs * 16;      // chunk x: [k-slab][width x 16]
+                if (G.cw(x) == 128) {
+                  push(base + (size_t)(8 * y) * 2048, 32768u);                // k-quarter y: 8 slabs of 128 x 16
+                } else {
+                  const int q0 = 2 * y, nq = min(2, NQ - q0);
+                  push(base + (size_t)(8 * q0) * 1024, (uint32_t)nq * 16384u); // two k-quarters: 16 slabs of 64 x 16
+                }
+              } else if (op == T2_OP_L3) {
+                push(w3 + (size_t)(G.ccol(x) >> 4) * np3 * 16, (uint32_t)((G.cw(x) >> 4) * np3) * 32u);
               }
             });
           }
@@ -334,108 +340,89 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             const uint32_t idesc_o = ptx::make_idesc_f16(128, np3);
             const uint32_t b3_step = (uint32_t)np3 * 2u;       // (np3 * 32 B) >> 4
             const uint32_t upar = units & 1u;
-            const int l1_per = max(1, min(NQ, 8 / k0s));
-            uint64_t l3_desc = 0;                              // current last-layer stage: descriptor, slot, piece range
-            int l3_slot = 0, l3_first = 0, l3_last = -1;
-            uint32_t sr_pre = 0;                               // an early test of the next piece's barrier is pending in t2_p_sr
+            uint64_t l1_desc = 0;                              // the held layer-1 weight stage
+            int l1_slot = 0;
+            int a1_waited = 0;                                 // a1r[0 .. a1_waited) have been observed
+            auto need_a1 = [&](int upto) {
+              while (a1_waited <= upto) { wait_epi(&misc->a1r[a1_waited], upar, 22); T2_TRACE(5 + a1_waited); ++a1_waited; }
+            };
 
             wait_epi(&misc->a0r, upar, 20);
             T2_TRACE(0);
-            t2_schedule(NQ, NJ, l1_per, [&](int op, int x, int y) {
-              if (op == T2_OP_L1) {
-                // layer-1 chunks [x, x + y): A0 (smem) x W1 chunk -> T(q)
-                const uint64_t bd = stage_take();
+            t2_schedule(G, [&](int op, int x, int y) {
+              if (op == T2_OP_L1_STAGE) {
+                l1_desc = stage_take();
+                l1_slot = slot;
+              } else if (op == T2_OP_L1) {
+                // layer-1 chunk x: A0 (smem) x W1 chunk -> L1 slot x & 1 (drained by the epilogue of chunk x - 2)
+                if (x >= 2) need_a1(x - 2);
                 ti = T2_CLOCK();
                 if (ptx::elect_one()) {
-                  for (int q = x; q < x + y; ++q) {
-                    const uint32_t d = tbase + (uint32_t)q * kT2Chunk;
-                    const uint64_t bq = bd + (uint64_t)((q - x) * k0s * 256);
-                    for (int i = 0; i < k0s; ++i)
-                      ptx::umma_f16(d, a0_desc + (uint64_t)(i * 256), bq + (uint64_t)(i * 256), idesc_l1, i > 0 ? 1u : 0u);
-                    ptx::umma_commit(&misc->l1f[q]);
-                  }
-                  ptx::umma_commit(&misc->empty[slot]);
+                  const uint32_t d = tbase + G.l1_col[x & 1];
+                  const uint64_t bq = l1_desc + (uint64_t)(x * k0s * 256);
+                  for (int i = 0; i < k0s; ++i)
+                    ptx::umma_f16(d, a0_desc + (uint64_t)(i * 256), bq + (uint64_t)(i * 256), idesc_l1, i > 0 ? 1u : 0u);
+                  ptx::umma_commit(&misc->l1f[x]);
+                  if (x == NQ - 1) ptx::umma_commit(&misc->empty[l1_slot]);
                 }
                 __syncwarp();
                 m_iss += T2_CLOCK() - ti;
                 T2_TRACE(1 + x);
-              } else if (op == T2_OP_WAIT_A1) {
-                for (int q = x; q < x + y; ++q) { wait_epi(&misc->a1r[q], upar, 22); T2_TRACE(5 + q); }
               } else if (op == T2_OP_L2) {
-                // layer-2 chunk x (hole x mod 3), k-half y: A1 quarters from TMEM T(q)[0:64] x 8 k-slabs of [64 x 16] each
-                const int hj = x % 3;
-                const int qa = y ? qh : 0, nq = y ? NQ - qh : qh;
-                const bool last_half = (y == (NQ > 1 ? 1 : 0));
-                // early readiness test of the piece consumed right after this chunk (overlaps with the MMAs below)
-                if (last_half && x >= 2 && x + 1 < NJ) {
-                  const int hn = (x + 1) % 3;
-                  asm volatile("mbarrier.test_wait.parity.shared::cta.b64 t2_p_sr, [%0], %1;" ::"r"(ptx::smem_u32(&misc->sr[hn])),
-                               "r"((ph_sr >> hn) & 1u) : "memory");
-                  sr_pre = 1;
-                }
-                if (x == 4) T2_TRACE(130 + 3 * y);
+                // layer-2 chunk x (slot x & 1), part y: A1 k-quarters from TMEM x k-slabs of [width x 16]
+                const int w = G.cw(x);
+                const int q0 = (w == 128) ? y : 2 * y;
+                const int nq = (w == 128) ? 1 : min(2, NQ - q0);
+                // the A1 quarters of this part, and a slot free of layer-1 accumulators (slot 0 hosted the even chunks)
+                need_a1(max(q0 + nq - 1, x == 0 ? ((NQ - 1) & ~1) : NQ - 1));
+                if (x == 3) T2_TRACE(130 + 3 * (y & 1));
                 const uint64_t bd = stage_take();
-                const int cur_slot = slot;
-                if (x == 4) T2_TRACE(131 + 3 * y);
+                if (x == 3) T2_TRACE(131 + 3 * (y & 1));
                 ti = T2_CLOCK();
-                const uint32_t d = tbase + t2_hole(hj);
                 if (ptx::elect_one()) {
-                  for (int qq = 0; qq < nq; ++qq) {
-                    const uint32_t at = tbase + (uint32_t)(qa + qq) * kT2Chunk;
-                    const uint64_t bq = bd + (uint64_t)(qq * 1024);
-                    ptx::umma_f16_ts(d, at, bq, idesc_l2, (qa + qq) > 0 ? 1u : 0u);
-                    ptx::umma_f16_ts(d, at + 8u, bq + 128u, idesc_l2, 1u);
-                    ptx::umma_f16_ts(d, at + 16u, bq + 256u, idesc_l2, 1u);
-                    ptx::umma_f16_ts(d, at + 24u, bq + 384u, idesc_l2, 1u);
-                    if (qq < nq - 1) {
-                      ptx::umma_f16_ts(d, at + 32u, bq + 512u, idesc_l2, 1u);
-                      ptx::umma_f16_ts(d, at + 40u, bq + 640u, idesc_l2, 1u);
-                      ptx::umma_f16_ts(d, at + 48u, bq + 768u, idesc_l2, 1u);
-                      ptx::umma_f16_ts(d, at + 56u, bq + 896u, idesc_l2, 1u);
+                  const uint32_t d = tbase + G.slot_col[x & 1];
+                  if (w == 128) {
+                    const uint32_t at = tbase + (uint32_t)q0 * 64u;
+                    ptx::umma_f16_ts(d, at, bd, idesc_l1, q0 > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bd + (uint64_t)(i * 256), idesc_l1, 1u);
+                  } else {
+                    for (int qq = 0; qq < nq; ++qq) {
+                      const uint32_t at = tbase + (uint32_t)(q0 + qq) * 64u;
+                      const uint64_t bq = bd + (uint64_t)(qq * 1024);
+                      ptx::umma_f16_ts(d, at, bq, idesc_l2, (q0 + qq) > 0 ? 1u : 0u);
+#pragma unroll
+                      for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bq + (uint64_t)(i * 128), idesc_l2, 1u);
                     }
                   }
-                }
-                __syncwarp();
-                stage_prefetch();                                      // a later stage always exists after a layer-2 op
-                if (ptx::elect_one()) {
-                  const uint32_t at = tbase + (uint32_t)(qa + nq - 1) * kT2Chunk + 32u;
-                  const uint64_t bq = bd + (uint64_t)((nq - 1) * 1024 + 512);
-                  ptx::umma_f16_ts(d, at, bq, idesc_l2, 1u);
-                  ptx::umma_f16_ts(d, at + 8u, bq + 128u, idesc_l2, 1u);
-                  ptx::umma_f16_ts(d, at + 16u, bq + 256u, idesc_l2, 1u);
-                  ptx::umma_f16_ts(d, at + 24u, bq + 384u, idesc_l2, 1u);
-                  ptx::umma_commit(&misc->empty[cur_slot]);
-                  if (last_half) ptx::umma_commit(&misc->l2f[hj]);     // chunk complete -> epilogue
+                  ptx::umma_commit(&misc->empty[slot]);
+                  if (q0 + nq == NQ) ptx::umma_commit(&misc->l2f[x & 1]);      // chunk complete -> epilogue
                 }
                 __syncwarp();
                 m_iss += T2_CLOCK() - ti;
-                if (x == 4) T2_TRACE(132 + 3 * y);
+                if (x == 3) T2_TRACE(132 + 3 * (y & 1));
               } else if (op == T2_OP_L2_DONE) {
                 T2_TRACE(10 + x);
-              } else if (op == T2_OP_L3_STAGE) {
-                l3_desc = stage_take();
-                l3_slot = slot; l3_first = x; l3_last = x + y - 1;
               } else {
-                // last layer, k-piece x held in hole x mod 3 (k-slab i = 8 packed columns at hole + 16 i) -> H(3)
-                const int hj = x % 3;
+                // last layer, k-piece x held packed in slot x & 1 (128-column chunk: 8 slabs at slot + 8 i; 64-column
+                // chunk: 4 slabs at slot + 16 i) -> last-layer accumulator
+                const int sl = x & 1;
+                const int w = G.cw(x);
                 if (x == 1) T2_TRACE(136);
                 ti = T2_CLOCK();
-                uint32_t sr_ok = 0;
-                if (sr_pre) asm volatile("selp.u32 %0, 1, 0, t2_p_sr;" : "=r"(sr_ok));
-                if (!sr_ok) ptx::mbar_wait(&misc->sr[hj], (ph_sr >> hj) & 1u, a.error_flag, 23);
+                ptx::mbar_wait(&misc->sr[sl], (ph_sr >> sl) & 1u, a.error_flag, 23);
                 ptx::tc_fence_after();
                 m_sr += T2_CLOCK() - ti;
-                ph_sr ^= 1u << hj;
-                sr_pre = 0;
+                ph_sr ^= 1u << sl;
                 if (x == 1) T2_TRACE(137);
+                const uint64_t bd = stage_take();
                 if (ptx::elect_one()) {
-                  const uint32_t at = tbase + t2_hole(hj), d = tbase + t2_hole(3);
-                  const uint64_t bd = l3_desc + (uint64_t)((uint32_t)(x - l3_first) * 4u * b3_step);
-                  ptx::umma_f16_ts(d, at, bd, idesc_o, x > 0 ? 1u : 0u);
-                  ptx::umma_f16_ts(d, at + 16u, bd + (uint64_t)b3_step, idesc_o, 1u);
-                  ptx::umma_f16_ts(d, at + 32u, bd + (uint64_t)(2 * b3_step), idesc_o, 1u);
-                  ptx::umma_f16_ts(d, at + 48u, bd + (uint64_t)(3 * b3_step), idesc_o, 1u);
-                  if (x == l3_last) ptx::umma_commit(&misc->empty[l3_slot]);
+                  const uint32_t at = tbase + G.slot_col[sl], d = tbase + G.la_col;
+                  const uint32_t astep = (w == 128) ? 8u : 16u;
+                  const int nsl = w >> 4;
+                  for (int i = 0; i < nsl; ++i)
+                    ptx::umma_f16_ts(d, at + astep * i, bd + (uint64_t)((uint32_t)i * b3_step), idesc_o, (x > 0 || i > 0) ? 1u : 0u);
+                  ptx::umma_commit(&misc->empty[slot]);
                   if (x == NJ - 1) ptx::umma_commit(&misc->l3f);
                 }
                 __syncwarp();
@@ -546,7 +533,6 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           for (int net = 0; net < md.nnets; ++net, ++units) {
             const int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
             const float* b1 = bias_s + g * 32;
-            const float* b2 = bias_s + md.h + g * 16;
             const float* bias = bias_s + 2 * md.h;
             const uint32_t upar = units & 1u;
             const int np3 = __ldg(&sd->layer[net][2].Np);
@@ -569,8 +555,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               }
             }
             t2_epi_bar();
-            // ---- layer 1: chunk q in T(q) (128 columns, 32 per thread) -> act -> fp16 pairs compacted into T(q)[0:64]
-            //      (A1 k-quarter q); the quadrant's four warps synchronise between reading and overwriting ----
+            // ---- layer 1: chunk q in L1 slot q & 1 (128 columns, 32 per thread) -> act -> fp16 pairs written to the A1
+            //      region [64 q, 64 q + 64) (a different TMEM region: no read / write hazard between the row's threads) ----
             for (int q = 0; q < NQ; ++q) {
               e_tmp = T2_CLOCK();
               t2_wait(&misc->l1f[q], upar, a.error_flag, 30, lane);
@@ -578,59 +564,63 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               e_w1 += T2_CLOCK() - e_tmp;
               ptx::tc_fence_after();
               e_tmp = T2_CLOCK();
-              const uint32_t tq = lane_base + (uint32_t)q * kT2Chunk;
-              const bool fine = tr && g == 0 && q == 1;     // fine-grained stamps of one chunk epilogue (ids 120..)
-              if (fine) T2_TRACE(120);
               uint32_t p[16];
               {
                 uint32_t r[32];
-                ptx::tmem_ld32(tq + (uint32_t)g * 32u, r);
+                ptx::tmem_ld32(lane_base + G.l1_col[q & 1] + (uint32_t)g * 32u, r);
                 ptx::tmem_ld_wait();
-                if (fine) T2_TRACE(121);
                 if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, b1 + q * kT2Chunk, p);
                 else               t2_act_pack32<2, TANH_MODE>(r, b1 + q * kT2Chunk, p);
               }
-              if (fine) T2_TRACE(122);
-              t2_quad_bar(quad);               // all four threads of the row have read their columns
-              if (fine) T2_TRACE(123);
-              ptx::tmem_st16(tq + (uint32_t)g * 16u, p);
+              ptx::tmem_st16(lane_base + (uint32_t)q * 64u + (uint32_t)g * 16u, p);
               ptx::tmem_st_wait();
-              if (fine) T2_TRACE(124);
               ptx::tc_fence_before();
               t2_warp_arrive(&misc->a1r[q], lane);
-              if (fine) T2_TRACE(125);
               if (tr) T2_TRACE(45 + 40 * (g & 1) + q);
               e_l1 += T2_CLOCK() - e_tmp;
             }
-            // ---- layer 2: 64-column chunk j in hole j mod 3 (16 columns per thread) -> act -> packed in place into the
-            //      first 8 of this thread's own columns = k-slab g of piece j of the last layer's A operand ----
-            {
-              int hj = 0;
-              for (int j = 0; j < NJ; ++j) {
-                e_tmp = T2_CLOCK();
-                t2_wait(&misc->l2f[hj], (ph_l2f >> hj) & 1u, a.error_flag, 31, lane);
-                ph_l2f ^= 1u << hj;
-                if (tr) T2_TRACE(50 + 40 * (g & 1) + j);
-                e_w2 += T2_CLOCK() - e_tmp;
-                ptx::tc_fence_after();
-                e_tmp = T2_CLOCK();
-                const uint32_t th = lane_base + t2_hole(hj) + (uint32_t)g * 16u;
+            // ---- layer 2: chunk j in slot j & 1 -> act -> fp16 pairs packed in place = k-piece j of the last layer's A
+            //      operand.  128-column chunk: 32 columns per thread compacted into slot[0:64) (the quadrant's four warps
+            //      synchronise between reading and overwriting); 64-column chunk: 16 columns per thread packed into the first
+            //      8 of the thread's own columns (no hazard) ----
+            for (int j = 0; j < NJ; ++j) {
+              const int sl = j & 1;
+              e_tmp = T2_CLOCK();
+              t2_wait(&misc->l2f[sl], (ph_l2f >> sl) & 1u, a.error_flag, 31, lane);
+              ph_l2f ^= 1u << sl;
+              if (tr) T2_TRACE(50 + 40 * (g & 1) + j);
+              e_w2 += T2_CLOCK() - e_tmp;
+              ptx::tc_fence_after();
+              e_tmp = T2_CLOCK();
+              const uint32_t sc = lane_base + G.slot_col[sl];
+              const float* bj = bias_s + md.h + G.ccol(j);
+              if (G.cw(j) == 128) {
+                uint32_t p[16];
+                {
+                  uint32_t r[32];
+                  ptx::tmem_ld32(sc + (uint32_t)g * 32u, r);
+                  ptx::tmem_ld_wait();
+                  if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, bj + g * 32, p);
+                  else               t2_act_pack32<2, TANH_MODE>(r, bj + g * 32, p);
+                }
+                t2_quad_bar(quad);             // all four threads of the row have read their columns
+                ptx::tmem_st16(sc + (uint32_t)g * 16u, p);
+              } else {
                 uint32_t p[8];
                 {
                   uint32_t r[16];
-                  ptx::tmem_ld16(th, r);
+                  ptx::tmem_ld16(sc + (uint32_t)g * 16u, r);
                   ptx::tmem_ld_wait();
-                  if (act_kind == 1) t2_act_pack16<1, TANH_MODE>(r, b2 + j * kT2Piece, p);
-                  else               t2_act_pack16<2, TANH_MODE>(r, b2 + j * kT2Piece, p);
+                  if (act_kind == 1) t2_act_pack16<1, TANH_MODE>(r, bj + g * 16, p);
+                  else               t2_act_pack16<2, TANH_MODE>(r, bj + g * 16, p);
                 }
-                ptx::tmem_st8(th, p);
-                ptx::tmem_st_wait();
-                ptx::tc_fence_before();
-                t2_warp_arrive(&misc->sr[hj], lane);
-                if (tr) T2_TRACE(60 + 40 * (g & 1) + j);
-                hj = (hj == 2) ? 0 : hj + 1;
-                e_l2 += T2_CLOCK() - e_tmp;
+                ptx::tmem_st8(sc + (uint32_t)g * 16u, p);
               }
+              ptx::tmem_st_wait();
+              ptx::tc_fence_before();
+              t2_warp_arrive(&misc->sr[sl], lane);
+              if (tr) T2_TRACE(60 + 40 * (g & 1) + j);
+              e_l2 += T2_CLOCK() - e_tmp;
             }
             // ---- last layer: coupling transform on this thread's 16-column slice of H(3); branch-free over the padded
             //      gather-order tables (padded entries hit the scratch column and are masked out of the log-det) ----
@@ -643,7 +633,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             const int c0 = g * 16;
             if (c0 < np3) {
               uint32_t r[16];
-              ptx::tmem_ld16(lane_base + t2_hole(3) + (uint32_t)c0, r);
+              ptx::tmem_ld16(lane_base + G.la_col + (uint32_t)c0, r);
               ptx::tmem_ld_wait();
               // every branch: gather the affected z2 columns first, store them last (see the gather above)
               if (md.kind == GBNF_KIND_GLOW && md.coupling == GBNF_COUPLING_AFFINE) {

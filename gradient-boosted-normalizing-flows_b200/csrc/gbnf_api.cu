@@ -118,7 +118,7 @@ int plan_layout(gbnf_ctx* h) {
           L.Kp = round_up(L.K_in, kq);
           L.Np = round_up(L.N_out, nq);
           if (!f16 && l > 0) L.Kp = round_up(c.h, kF32KT);
-          L.NC = L.Np;
+          L.NC = L.Np; L.NC2 = 0;
           L.w_off = w; w += (long long)L.Kp * L.Np;
           L.b_off = f; f += round_up_ll(L.Np, 4);
           if (l == 0) kp0_max = std::max(kp0_max, L.Kp);
@@ -150,7 +150,10 @@ int plan_layout(gbnf_ctx* h) {
     if (h->tc2) {
       if (!tc2_make_plan(md, h->steps_h, &h->tc)) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: shared memory budget exceeded");
       for (StepDesc& sd : h->steps_h)
-        for (int net = 0; net < md.nnets; ++net) { sd.layer[net][0].NC = kT2Chunk; sd.layer[net][1].NC = kT2Piece; }
+        for (int net = 0; net < md.nnets; ++net) {
+          sd.layer[net][0].NC = kT2Chunk;
+          sd.layer[net][1].NC = kT2Chunk; sd.layer[net][1].NC2 = (md.h == 512) ? kT2Piece : 0;
+        }
     } else if (!tc_make_plan(md, h->steps_h, &h->tc, &why)) {
       return fail(GBNF_ERR_INVALID, "f16 tensor-core path: " + why);
     }

@@ -128,13 +128,17 @@ __global__ void pack_weight_f16_kernel(const float* __restrict__ W, const float*
   const long long total = (long long)ld.Kp * ld.Np;
   __half* dst = wblob + ld.w_off;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    // decode destination index -> (n, k): [N chunk][k-slab][NC/8 row groups][2 k-chunks][8 rows][8 halves]
-    const int slab_elems = ld.NC * 16, nslabs = ld.Kp >> 4;
-    const long long cs = i / slab_elems;
-    const int chunk = (int)(cs / nslabs), slab = (int)(cs % nslabs);
-    const int r = (int)(i % slab_elems);
-    const int grp = r / 128, kc = (r % 128) / 64, row = (r % 64) / 8, e = r % 8;
-    const int n = chunk * ld.NC + grp * 8 + row, k = slab * 16 + kc * 8 + e;
+    // decode destination index -> (n, k): [N chunk][k-slab][width/8 row groups][2 k-chunks][8 rows][8 halves], chunk widths
+    // alternating NC, NC2
+    const int nce = ld.NC, nco = ld.NC2 ? ld.NC2 : ld.NC;
+    const long long pair_elems = (long long)(nce + nco) * ld.Kp;
+    const long long pr = i / pair_elems;
+    long long r = i % pair_elems;
+    int w = nce, col0 = (int)pr * (nce + nco);
+    if (r >= (long long)nce * ld.Kp) { r -= (long long)nce * ld.Kp; w = nco; col0 += nce; }
+    const int slab = (int)(r / (w * 16)), rr = (int)(r % (w * 16));
+    const int grp = rr / 128, kc = (rr % 128) / 64, row = (rr % 64) / 8, e = rr % 8;
+    const int n = col0 + grp * 8 + row, k = slab * 16 + kc * 8 + e;
     float v = (k < ld.K_in && n < ld.N_out) ? W[(long long)n * ld.K_in + k] : 0.f;
     __half hv = __float2half_rn(v);
     if (__hisinf(hv) || __hisnan(hv)) *overflow = 1;

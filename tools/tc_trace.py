@@ -11,7 +11,9 @@ mode = sys.argv[2] if len(sys.argv) > 2 else "f16fast"
 cfg = bench.CONFIGS[cfg_name]
 dev = torch.device("cuda", 0)
 torch.manual_seed(1)
-model = gbnf_b200.BoostedFlow(bench.make_args(cfg, dev), gemm_mode=mode).to(dev)
+margs = bench.make_args(cfg, dev)
+margs.coupling_network = os.environ.get('GBNF_PROF_ACT', margs.coupling_network)
+model = gbnf_b200.BoostedFlow(margs, gemm_mode=mode).to(dev)
 x = torch.randn((65536, cfg["D"]), device=dev)
 model.train()
 with torch.no_grad():
