@@ -1,34 +1,34 @@
 // Pipelined tcgen05 / TMEM / bulk-TMA coupling-stack kernel (GBNF_GEMM_F16_TC*, coupling_network_depth == 1,
 // hidden width a multiple of 128 up to 512).  Rows, activations and accumulators never leave the SM, and -- unlike
-// coupling_tc.cuh -- the hidden activations never touch SHARED memory either: they are packed to fp16 in place in
-// tensor memory and fed back to tcgen05.mma as the A operand from TMEM.  Shared memory then only carries the weight
-// stream (written once by TMA, read once by the tensor pipe), which is what bounds a 128-row tile on one SM
-// (measured: 128 B/clk of shared-memory bandwidth, 42 B/clk of L2->SM ingest, tools/tc_probe2.cu).
+// coupling_tc.cuh -- the hidden activations never touch SHARED memory either: they are packed to fp16 in tensor memory
+// and fed back to tcgen05.mma as the A operand from TMEM.  Shared memory then only carries the weight stream (written
+// once by TMA, read once by the tensor pipe), which is what bounds a 128-row tile on one SM (measured: 128 B/clk of
+// shared-memory bandwidth, 42 B/clk of L2->SM ingest, tools/tc_probe2.cu).
 //
-//   TMEM map (512 columns), T(q) = [128 q, 128 q + 128), q = 0..3, NQ = h / 128:
-//     layer 1 (K = |z1|, A0 from smem):  chunk q (128 columns) -> T(q); epilogue: tanh -> fp16 pairs -> T(q)[0:64]
-//                                        = k-quarter q of the layer-2 A operand ("A1"), leaving the hole H(q) = T(q)[64:128]
-//     layer 2 (K = h, A1 from TMEM):     64-column chunk j -> hole H(j mod 3); chunk 0 is accumulated k-quarter by
-//                                        k-quarter right behind the layer-1 epilogue, later chunks run up to three ahead
-//                                        of the epilogue;  epilogue: tanh -> fp16 pairs in place (hole[0:32])
-//                                        = k-piece j of the last layer's A operand
-//     last layer (N <= 64, A2 from TMEM): K-streamed piece by piece into H(3)
+//   TMEM map (512 columns, T2Geom below):
+//     A1 = columns [0, h/2): the layer-2 A operand, k-quarter q (128 K elements) at [64 q, 64 q + 64)
+//     two accumulator slots after it (128 + 128 columns; 128 + 64 when h = 512) and the last-layer accumulator (64)
+//     layer 1 (K = |z1|, A0 from smem):  chunk q (N = 128) -> L1 slot q & 1; epilogue: bias + act -> fp16 pairs -> A1 quarter q
+//     layer 2 (K = h, A1 from TMEM):     chunk j (N = 128 or 64) -> slot j & 1; chunk 0 is accumulated k-quarter by k-quarter
+//                                        behind the layer-1 epilogue, later chunks run one ahead of the epilogue;
+//                                        epilogue: bias + act -> fp16 pairs packed IN PLACE = k-piece j of the last layer's A
+//     last layer (N <= 64, A2 from TMEM): K-streamed piece by piece into the last-layer accumulator
 //   Every reuse of a TMEM region is ordered either by the in-order tensor pipe or by an epilogue -> MMA mbarrier.
 //
-//   weights: layer 1 [128-col chunk][k-slab][128 x 16], layer 2 [64-col chunk][k-slab][64 x 16], last layer
-//   [k-slab][Np x 16], fp16 canonical K-major slabs; one ring stage (<= 16 KB) = one L1 chunk, one (chunk, k-quarter)
-//   of L2, or the 4 k-slabs of one last-layer piece.  Producer and MMA warp walk the same fixed schedule.
+//   weights: layer 1 [128-col chunk][k-slab][128 x 16], layer 2 [chunk (128 / 64 wide)][k-slab][width x 16], last layer
+//   [k-slab][Np x 16], fp16 canonical K-major slabs; one ring stage (<= 32 KB) = W1 of all layer-1 chunks, 32 KB of one
+//   layer-2 chunk, or the k-slabs of one last-layer piece.  Producer and MMA warp walk the same fixed schedule.
 //
-// Warp roles: warp 0 = TMA producer (+ L1 prefetch of the step's bias / table lines), warp 1 = MMA issuer (both run
-// warp-uniform control flow and issue from one elected lane, see ptx::elect_one), warps 2..9 = epilogue (two threads
-// per row, splitting every chunk's columns).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (both run warp-uniform control flow and issue from one elected
+// lane, see ptx::elect_one), warps 2..17 = epilogue: four threads per row (column groups g = 0..3), each TMEM lane
+// quadrant served by four warps.
 #pragma once
 #include "coupling_tc.cuh"
 
 namespace gbnf {
 
-constexpr int kT2Chunk = 128;        // layer-1 chunk = k-quarter of layer 2
-constexpr int kT2Piece = 64;         // layer-2 chunk = k-piece of the last layer
+constexpr int kT2Chunk = 128;        // layer-1 chunk = k-quarter of layer 2 = wide layer-2 chunk
+constexpr int kT2Piece = 64;         // narrow layer-2 chunk (h = 512 only)
 constexpr int kT2Threads = 576;       // 2 control warps + 16 epilogue warps
 constexpr int kT2EpiThreads = 512;
 constexpr int kT2MaxStages = 8;
@@ -46,6 +46,7 @@ struct Tc2Misc {
   uint64_t l3f;       // MMA -> epilogue : last layer accumulated
   uint32_t tmem_base;
   uint32_t last_flag;
+  int meta[2][8];     // per step (double buffered): in_dim, out_dim, Kp of layer 1, Np of the last layer (net 0, 1), bias offsets
   float coef[kMaxComponents];
   float part[3 * kTcRows];
   float part2[3 * kTcRows];
@@ -89,8 +90,6 @@ inline bool tc2_make_plan(const ModelDims& md, const std::vector<StepDesc>& step
   return p->nst >= 4;
 }
 
-__device__ __forceinline__ uint32_t t2_hole(int i) { return 64u + 128u * (uint32_t)i; }
-
 // Epilogue warp -> MMA warp handoff: every lane has fenced its own writes, one lane arrives for the warp.
 __device__ __forceinline__ void t2_warp_arrive(uint64_t* bar, int lane) {
   __syncwarp();
@@ -98,7 +97,8 @@ __device__ __forceinline__ void t2_warp_arrive(uint64_t* bar, int lane) {
 }
 // mbarrier wait polled by one lane per warp (256 spinning threads would compete with the MMA operand reads for shared memory)
 __device__ __forceinline__ void t2_wait(uint64_t* bar, uint32_t parity, int* err, int code, int lane) {
-  if (lane == 0) ptx::mbar_wait(bar, parity, err, code);
+  (void)lane;
+  ptx::mbar_wait(bar, parity, err, code);   // all lanes poll: ~50 cycles less latency than one polling lane + __syncwarp
   __syncwarp();
 }
 // the four epilogue warps that share a TMEM lane quadrant (= the four threads of every row in it)
@@ -182,6 +182,16 @@ __device__ __forceinline__ void t2_schedule(const T2Geom& g, F&& f) {
 #define T2_CLOCK() (PROF == 1 ? clock64() : 0LL)
 // event trace of ONE coupling pass (unit kT2TraceUnit of CTA 0): a.prof[32 + id] = clock64(), see tools/tc_trace.py
 #define T2_TRACE(id) do { if (PROF && a.prof != nullptr && blockIdx.x == 0 && units == kT2TraceUnit && lane == 0) a.prof[32 + (id)] = clock64(); } while (0)
+// One thread copies the scalars of a step's descriptor that the epilogue needs into shared memory a step ahead: a
+// first-touch global load at the start of a step would sit on the critical path of every coupling pass.
+__device__ __forceinline__ void t2_stage_meta(const StepDesc* sd, int nnets, int* m) {
+  const int v0 = __ldg(&sd->in_dim), v1 = __ldg(&sd->out_dim), v2 = __ldg(&sd->layer[0][0].Kp);
+  const int v3 = __ldg(&sd->layer[0][2].Np), v5 = (int)__ldg(&sd->layer[0][0].b_off);
+  int v4 = 0, v6 = 0;
+  if (nnets == 2) { v4 = __ldg(&sd->layer[1][2].Np); v6 = (int)__ldg(&sd->layer[1][0].b_off); }
+  m[0] = v0; m[1] = v1; m[2] = v2; m[3] = v3; m[4] = v4; m[5] = v5; m[6] = v6;
+}
+
 template <int TANH_MODE, int PROF>   // PROF: 0 production, 1 cycle counters + event trace, 2 event trace only (near-production timing)
 __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArgs a, TcPlan plan) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -343,18 +353,19 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             uint64_t l1_desc = 0;                              // the held layer-1 weight stage
             int l1_slot = 0;
             int a1_waited = 0;                                 // a1r[0 .. a1_waited) have been observed
+            uint32_t sr_pre = 0;                               // an early test of the next piece's barrier is pending in t2_p_sr
             auto need_a1 = [&](int upto) {
               while (a1_waited <= upto) { wait_epi(&misc->a1r[a1_waited], upar, 22); T2_TRACE(5 + a1_waited); ++a1_waited; }
             };
 
-            wait_epi(&misc->a0r, upar, 20);
-            T2_TRACE(0);
             t2_schedule(G, [&](int op, int x, int y) {
               if (op == T2_OP_L1_STAGE) {
                 l1_desc = stage_take();
                 l1_slot = slot;
+                T2_TRACE(138);
               } else if (op == T2_OP_L1) {
                 // layer-1 chunk x: A0 (smem) x W1 chunk -> L1 slot x & 1 (drained by the epilogue of chunk x - 2)
+                if (x == 0) { wait_epi(&misc->a0r, upar, 20); T2_TRACE(0); }   // A0 gathered, TMEM of the previous pass drained
                 if (x >= 2) need_a1(x - 2);
                 ti = T2_CLOCK();
                 if (ptx::elect_one()) {
@@ -377,7 +388,17 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 need_a1(max(q0 + nq - 1, x == 0 ? ((NQ - 1) & ~1) : NQ - 1));
                 if (x == 3) T2_TRACE(130 + 3 * (y & 1));
                 const uint64_t bd = stage_take();
+                const int cur_slot = slot;
                 if (x == 3) T2_TRACE(131 + 3 * (y & 1));
+                // The op after the LAST part of chunk x >= 1 is the last-layer piece x - 1: test its barrier and take its weight
+                // stage now, so that this bookkeeping overlaps with the MMAs issued below instead of idling the pipe.
+                const bool pre_l3 = (q0 + nq == NQ) && x >= 1;
+                if (pre_l3) {
+                  const int sn = (x - 1) & 1;
+                  asm volatile("mbarrier.test_wait.parity.shared::cta.b64 t2_p_sr, [%0], %1;" ::"r"(ptx::smem_u32(&misc->sr[sn])),
+                               "r"((ph_sr >> sn) & 1u) : "memory");
+                  sr_pre = 1;
+                }
                 ti = T2_CLOCK();
                 if (ptx::elect_one()) {
                   const uint32_t d = tbase + G.slot_col[x & 1];
@@ -395,10 +416,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                       for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bq + (uint64_t)(i * 128), idesc_l2, 1u);
                     }
                   }
-                  ptx::umma_commit(&misc->empty[slot]);
+                  ptx::umma_commit(&misc->empty[cur_slot]);
                   if (q0 + nq == NQ) ptx::umma_commit(&misc->l2f[x & 1]);      // chunk complete -> epilogue
                 }
                 __syncwarp();
+                if (pre_l3) stage_prefetch();                                  // the piece's weights (queued MMAs hide this)
                 m_iss += T2_CLOCK() - ti;
                 if (x == 3) T2_TRACE(132 + 3 * (y & 1));
               } else if (op == T2_OP_L2_DONE) {
@@ -410,7 +432,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 const int w = G.cw(x);
                 if (x == 1) T2_TRACE(136);
                 ti = T2_CLOCK();
-                ptx::mbar_wait(&misc->sr[sl], (ph_sr >> sl) & 1u, a.error_flag, 23);
+                uint32_t sr_ok = 0;
+                if (sr_pre) asm volatile("selp.u32 %0, 1, 0, t2_p_sr;" : "=r"(sr_ok));
+                sr_pre = 0;
+                if (!sr_ok) ptx::mbar_wait(&misc->sr[sl], (ph_sr >> sl) & 1u, a.error_flag, 23);
                 ptx::tc_fence_after();
                 m_sr += T2_CLOCK() - ti;
                 ph_sr ^= 1u << sl;
@@ -455,6 +480,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     if (blockIdx.x < a.num_units && et < 2 * kEpPad) {
       const int cb0 = a.c0 + ((int)blockIdx.x % a.split) * a.comps_per_unit;
       tab_s[et] = __ldg(reinterpret_cast<const float4*>(a.fblob + a.steps[cb0 * md.K].ep_off) + et);
+      if (et == 0) t2_stage_meta(a.steps + cb0 * md.K, md.nnets, misc->meta[0]);
     }
     const bool tr = (warp_e & 3) == 0;     // one tracing warp per group
     const long long e_t0 = T2_CLOCK();
@@ -498,7 +524,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
         for (int k = 0; k < md.K; ++k, ++stepc) {
           e_tmp = T2_CLOCK();
           const StepDesc* sd = a.steps + (c * md.K + k);
-          const int out_dim = __ldg(&sd->out_dim), in_dim = __ldg(&sd->in_dim);
+          const int* meta = misc->meta[stepc & 1u];                          // staged a step ahead
+          const int out_dim = meta[1], in_dim = meta[0];
           const float4* tab1 = tab_s + (stepc & 1u) * (2 * kEpPad);          // staged by the previous step
           const float4* tab2 = tab1 + kEpPad;
           // the step after this one (next k, next component, or the first step of this CTA's next tile)
@@ -509,7 +536,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                                         : nullptr;
           // ---- ActNorm / eval-BatchNorm affine fused into the gather of z1 -> A0 (fp16, canonical layout, zero padded) ----
           {
-            const int nch = __ldg(&sd->layer[0][0].Kp) >> 3;                // 8-element chunks
+            const int nch = meta[2] >> 3;                                    // 8-element chunks
             for (int ch = g; ch < nch; ch += 4) {
               // loads first, stores last: the compiler cannot prove that the gathered columns are distinct, so an
               // interleaved load / store sequence would be serialised on shared-memory latency
@@ -535,7 +562,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             const float* b1 = bias_s + g * 32;
             const float* bias = bias_s + 2 * md.h;
             const uint32_t upar = units & 1u;
-            const int np3 = __ldg(&sd->layer[net][2].Np);
+            const int np3 = meta[3 + net];
             // hand A0 (and every drained TMEM region) to the MMA warp
             ptx::fence_proxy_async_smem();
             ptx::tc_fence_before();
@@ -546,13 +573,14 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             //      all four warps of a scheduler at once for an L2 round trip ----
             t2_epi_bar();                              // nobody still reads the previous pass's biases
             {
-              const float4* bsrc = reinterpret_cast<const float4*>(a.fblob + __ldg(&sd->layer[net][0].b_off));
+              const float4* bsrc = reinterpret_cast<const float4*>(a.fblob + meta[5 + net]);
               const int nb4 = (2 * md.h + np3) >> 2;
               for (int i = et; i < nb4; i += kT2EpiThreads) reinterpret_cast<float4*>(bias_s)[i] = __ldg(bsrc + i);
               if (net == 0 && sd_next != nullptr && et >= kT2EpiThreads - 2 * kEpPad) {
                 const int i = et - (kT2EpiThreads - 2 * kEpPad);
                 tab_s[((stepc + 1) & 1u) * (2 * kEpPad) + i] = __ldg(reinterpret_cast<const float4*>(a.fblob + __ldg(&sd_next->ep_off)) + i);
               }
+              if (net == 0 && sd_next != nullptr && et == 0) t2_stage_meta(sd_next, md.nnets, misc->meta[(stepc + 1) & 1u]);
             }
             t2_epi_bar();
             // ---- layer 1: chunk q in L1 slot q & 1 (128 columns, 32 per thread) -> act -> fp16 pairs written to the A1
