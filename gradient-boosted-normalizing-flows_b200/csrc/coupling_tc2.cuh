@@ -140,6 +140,8 @@ __device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const flo
 struct T2Geom {
   int NQ, NJ;
   bool tight;
+  bool l1_in_slot0;     // layer-1 accumulators share accumulator slot 0 (then layer-2 chunk 0 must wait for them to drain)
+  bool l1_even_inplace; // the even layer-1 chunks accumulate inside the A1 region they are packed into
   uint32_t slot_col[2], l1_col[2], la_col;
   __device__ __forceinline__ int cw(int j) const { return (tight && (j & 1)) ? 64 : 128; }
   __device__ __forceinline__ int ccol(int j) const { return tight ? 192 * (j >> 1) + ((j & 1) ? 128 : 0) : 128 * j; }
@@ -151,8 +153,14 @@ __device__ __forceinline__ T2Geom t2_geom(int h) {
   g.NJ = g.tight ? 5 : g.NQ;
   const uint32_t a1w = (uint32_t)h >> 1;
   g.slot_col[0] = a1w; g.slot_col[1] = a1w + 128u;
-  g.l1_col[0] = a1w;   g.l1_col[1] = a1w + 128u;
   g.la_col = g.tight ? 448u : a1w + 256u;
+  // Layer-1 accumulators (128 columns each, two in flight).  Keeping them OUT of slot 0 lets layer-2 chunk 0 start as soon as
+  // the first A1 quarter exists.  h = 512: even chunks use the upper half of the A1 region itself ([128, 256): still unused
+  // when chunk 0 accumulates, packed in place by chunk 2), odd chunks use slot 1 + the last-layer accumulator ([384, 512)).
+  // h <= 256: slot 1 and the columns behind it are free.  h = 384 has no spare 128 columns: slots 0 / 1 as before.
+  if (g.tight)        { g.l1_col[0] = 128u; g.l1_col[1] = 384u; g.l1_in_slot0 = false; g.l1_even_inplace = true; }
+  else if (h <= 256)  { g.l1_col[0] = a1w + 128u; g.l1_col[1] = a1w + 256u; g.l1_in_slot0 = false; g.l1_even_inplace = false; }
+  else                { g.l1_col[0] = a1w; g.l1_col[1] = a1w + 128u; g.l1_in_slot0 = true; g.l1_even_inplace = false; }
   return g;
 }
 
@@ -167,8 +175,16 @@ enum { T2_OP_L1_STAGE = 0, T2_OP_L1, T2_OP_L2, T2_OP_L2_DONE, T2_OP_L3 };
 template <class F>
 __device__ __forceinline__ void t2_schedule(const T2Geom& g, F&& f) {
   f(T2_OP_L1_STAGE, 0, 0);
-  for (int q = 0; q < g.NQ; ++q) f(T2_OP_L1, q, 0);
-  for (int j = 0; j < g.NJ; ++j) {
+  f(T2_OP_L1, 0, 0);
+  if (g.NQ > 1) f(T2_OP_L1, 1, 0);
+  // chunk 0 (always 128 wide: one part per k-quarter) is interleaved with the remaining layer-1 chunks, so that its part q is
+  // issued as soon as A1 quarter q exists
+  for (int q = 0; q < g.NQ; ++q) {
+    if (q + 2 < g.NQ) f(T2_OP_L1, q + 2, 0);
+    f(T2_OP_L2, 0, q);
+  }
+  f(T2_OP_L2_DONE, 0, 0);
+  for (int j = 1; j < g.NJ; ++j) {
     if (j >= 2) f(T2_OP_L3, j - 2, 0);                       // frees slot j & 1
     const int parts = (g.cw(j) == 128) ? g.NQ : (g.NQ + 1) / 2;
     for (int p = 0; p < parts; ++p) f(T2_OP_L2, j, p);
@@ -385,7 +401,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 const int q0 = (w == 128) ? y : 2 * y;
                 const int nq = (w == 128) ? 1 : min(2, NQ - q0);
                 // the A1 quarters of this part, and a slot free of layer-1 accumulators (slot 0 hosted the even chunks)
-                need_a1(max(q0 + nq - 1, x == 0 ? ((NQ - 1) & ~1) : NQ - 1));
+                need_a1(max(q0 + nq - 1, x == 0 ? (G.l1_in_slot0 ? ((NQ - 1) & ~1) : 0) : NQ - 1));
                 if (x == 3) T2_TRACE(130 + 3 * (y & 1));
                 const uint64_t bd = stage_take();
                 const int cur_slot = slot;
@@ -584,7 +600,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             }
             t2_epi_bar();
             // ---- layer 1: chunk q in L1 slot q & 1 (128 columns, 32 per thread) -> act -> fp16 pairs written to the A1
-            //      region [64 q, 64 q + 64) (a different TMEM region: no read / write hazard between the row's threads) ----
+            //      region [64 q, 64 q + 64) (normally a different TMEM region; see T2Geom::l1_even_inplace) ----
             for (int q = 0; q < NQ; ++q) {
               e_tmp = T2_CLOCK();
               t2_wait(&misc->l1f[q], upar, a.error_flag, 30, lane);
@@ -600,6 +616,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, b1 + q * kT2Chunk, p);
                 else               t2_act_pack32<2, TANH_MODE>(r, b1 + q * kT2Chunk, p);
               }
+              if (G.l1_even_inplace && !(q & 1)) t2_quad_bar(quad);   // packed quarter may overlap the row's unread accumulator
               ptx::tmem_st16(lane_base + (uint32_t)q * 64u + (uint32_t)g * 16u, p);
               ptx::tmem_st_wait();
               ptx::tc_fence_before();
