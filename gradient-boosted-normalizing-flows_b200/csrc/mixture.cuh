@@ -7,6 +7,41 @@ namespace gbnf {
 
 constexpr int kMixThreads = 256;
 
+// rows of n <= 4 NV terms, 128-bit loads, two rows per iteration
+template <int NV>
+__device__ __forceinline__ float mixture_row_lse(const float4 (&v)[NV], int n, const float* coef) {
+  float t[4 * NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { t[4 * i] = v[i].x; t[4 * i + 1] = v[i].y; t[4 * i + 2] = v[i].z; t[4 * i + 3] = v[i].w; }
+  float m = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 4 * NV; ++c) { t[c] = (c < n) ? t[c] + coef[c] : -INFINITY; m = fmaxf(m, t[c]); }
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4 * NV; ++c) sum += __expf(t[c] - m);                // exp(-inf) = 0 for skipped / padded terms
+  return (m == -INFINITY) ? 0.f : m + __logf(sum);
+}
+template <int NV>
+__device__ __forceinline__ void mixture_rows_small(const float* __restrict__ logq, long long B, int ld, int n, const float* coef,
+                                                   float* __restrict__ G_ll, long long stride) {
+  long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; b + stride < B; b += 2 * stride) {
+    float4 v0[NV], v1[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v0[i] = __ldg(reinterpret_cast<const float4*>(logq + b * ld) + i);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v1[i] = __ldg(reinterpret_cast<const float4*>(logq + (b + stride) * ld) + i);
+    G_ll[b] = mixture_row_lse<NV>(v0, n, coef);
+    G_ll[b + stride] = mixture_row_lse<NV>(v1, n, coef);
+  }
+  if (b < B) {
+    float4 v0[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v0[i] = __ldg(reinterpret_cast<const float4*>(logq + b * ld) + i);
+    G_ll[b] = mixture_row_lse<NV>(v0, n, coef);
+  }
+}
+
 // ---- G_ll[b] = logsumexp_c(coef[c] + logq[b, c]) ---------------------------------------------------------
 // One thread per row; a warp reads 32 consecutive rows = one contiguous span of 32*ld floats.  With ld % 4 == 0
 // the row is fetched with 128-bit loads.
@@ -17,7 +52,17 @@ __global__ void __launch_bounds__(kMixThreads) mixture_lse_kernel(const float* _
   if (threadIdx.x == 0) mixture_coefficients(rho, n, skip_c, mix_mode, coef);
   __syncthreads();
   const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logq) & 15) == 0);
-  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (vec && n <= 16) {
+    // all terms of a row in registers: exact max, then one ex2 per term and one lg2 per row (MUFU); two rows in flight
+    const int nv = (n + 3) >> 2;
+    if (nv == 1) mixture_rows_small<1>(logq, B, ld, n, coef, G_ll, stride);
+    else if (nv == 2) mixture_rows_small<2>(logq, B, ld, n, coef, G_ll, stride);
+    else if (nv == 3) mixture_rows_small<3>(logq, B, ld, n, coef, G_ll, stride);
+    else mixture_rows_small<4>(logq, B, ld, n, coef, G_ll, stride);
+    return;
+  }
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += stride) {
     const float* row = logq + b * ld;
     OnlineLse o; o.init();
     int c = 0;
@@ -77,8 +122,16 @@ __global__ void __launch_bounds__(kMixThreads) softmax_stats_kernel(const float*
   MsPair v; v.m = -INFINITY; v.s = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  for (long long i = i0; i < B; i += stride) v.m = fmaxf(v.m, -__ldg(G_ll + i));
-  for (long long i = i0; i < B; i += stride) v.s += expf(-__ldg(G_ll + i) - v.m);
+  const bool vec = (reinterpret_cast<uintptr_t>(G_ll) & 15) == 0;
+  const long long B4 = vec ? (B >> 2) : 0;                                 // 128-bit body, scalar tail
+  const float4* G4 = reinterpret_cast<const float4*>(G_ll);
+  for (long long i = i0; i < B4; i += stride) { const float4 g = __ldg(G4 + i); v.m = fmaxf(v.m, -fminf(fminf(g.x, g.y), fminf(g.z, g.w))); }
+  for (long long i = 4 * B4 + i0; i < B; i += stride) v.m = fmaxf(v.m, -__ldg(G_ll + i));
+  for (long long i = i0; i < B4; i += stride) {
+    const float4 g = __ldg(G4 + i);                                        // second sweep: L2 hits for batch-sized inputs
+    v.s += (expf(-g.x - v.m) + expf(-g.y - v.m)) + (expf(-g.z - v.m) + expf(-g.w - v.m));
+  }
+  for (long long i = 4 * B4 + i0; i < B; i += stride) v.s += expf(-__ldg(G_ll + i) - v.m);
   MsPair r = ms_block_reduce(v, sm);
   if (threadIdx.x == 0) {
     partial[2 * blockIdx.x] = r.m;
@@ -113,7 +166,22 @@ __global__ void __launch_bounds__(kMixThreads) weight_apply_kernel(const float* 
   const float wmax = 1.0f / S;
   const bool clamp = wmax > hi;
   double acc = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(G_ll) | reinterpret_cast<uintptr_t>(w)) & 15) == 0;
+  const long long B4 = vec ? (B >> 2) : 0;                                 // 128-bit body, scalar tail
+  for (long long i = i0; i < B4; i += stride) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(G_ll) + i);
+    float4 v;
+    v.x = expf(-g.x - M) / S; v.y = expf(-g.y - M) / S; v.z = expf(-g.z - M) / S; v.w = expf(-g.w - M) / S;
+    if (clamp) {
+      v.x = fmaxf(fminf(v.x, hi), lo); v.y = fmaxf(fminf(v.y, hi), lo);
+      v.z = fmaxf(fminf(v.z, hi), lo); v.w = fmaxf(fminf(v.w, hi), lo);
+    }
+    reinterpret_cast<float4*>(w)[i] = v;
+    acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+  }
+  for (long long i = 4 * B4 + i0; i < B; i += stride) {
     float v = expf(-__ldg(G_ll + i) - M) / S;
     if (clamp) v = fmaxf(fminf(v, hi), lo);
     w[i] = v;
@@ -139,8 +207,15 @@ __global__ void __launch_bounds__(kMixThreads) weight_renorm_kernel(float* __res
   const float s = (float)(*wsum);
   if (stats_opt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) stats_opt[3] = s;
   if (!always && s == 1.0f) return;            // `if weights.sum() != 1.0` density_experiment.py:640 (toy: always)
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x)
-    w[i] = w[i] / s;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long B4 = ((reinterpret_cast<uintptr_t>(w) & 15) == 0) ? (B >> 2) : 0;
+  for (long long i = i0; i < B4; i += stride) {
+    float4 v = reinterpret_cast<float4*>(w)[i];
+    v.x = v.x / s; v.y = v.y / s; v.z = v.z / s; v.w = v.w / s;
+    reinterpret_cast<float4*>(w)[i] = v;
+  }
+  for (long long i = 4 * B4 + i0; i < B; i += stride) w[i] = w[i] / s;
 }
 
 __global__ void zero_double_kernel(double* p) { *p = 0.0; }
