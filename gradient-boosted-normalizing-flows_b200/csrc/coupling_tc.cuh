@@ -33,7 +33,7 @@ struct TcPlan {
   int K0p = 0;                 // padded layer-0 K (max over steps)
   int out_max = 0;
   int tanh_mode = 1;           // 0: MUFU.TANH (tanh.approx.f32), 1: 1 - 2/(1+2^(2x log2 e)) via ex2.approx + rcp.approx
-  uint32_t off_zs = 0, off_a0 = 0, off_a1 = 0, off_ring = 0, off_sh = 0, off_misc = 0, off_bias = 0, off_tab = 0;
+  uint32_t off_zs = 0, off_a0 = 0, off_a1 = 0, off_ring = 0, off_sh = 0, off_misc = 0, off_bias = 0, off_tab = 0, off_w3 = 0;
   size_t smem_bytes = 0;
   int tmem_cols = 512;
 };

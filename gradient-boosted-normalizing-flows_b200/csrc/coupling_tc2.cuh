@@ -32,6 +32,7 @@ constexpr int kT2Piece = 64;         // narrow layer-2 chunk (h = 512 only)
 constexpr int kT2Threads = 576;       // 2 control warps + 16 epilogue warps
 constexpr int kT2EpiThreads = 512;
 constexpr int kT2MaxStages = 8;
+constexpr uint32_t kT2W3Bytes = 16384;      // one last-layer piece: <= 8 k-slabs of [64 x 16]
 constexpr uint32_t kT2StageBytes = 32768;   // ring slot: up to 16 layer-2 k-slabs; fewer, larger handshakes (see acquire())
 constexpr uint32_t kT2TraceUnit = 37;
 
@@ -44,6 +45,8 @@ struct Tc2Misc {
   uint64_t l1f[4];    // MMA -> epilogue : layer-1 chunk q accumulated        (tcgen05.commit)
   uint64_t l2f[3];    // MMA -> epilogue : layer-2 chunk in hole i accumulated
   uint64_t l3f;       // MMA -> epilogue : last layer accumulated
+  uint64_t w3full[2]; // producer -> MMA : last-layer weights of a piece landed in their own double buffer (outside the ring)
+  uint64_t w3empty[2];// MMA -> producer : that buffer may be refilled
   uint32_t tmem_base;
   uint32_t last_flag;
   int meta[2][8];     // per step (double buffered): in_dim, out_dim, Kp of layer 1, Np of the last layer (net 0, 1), bias offsets
@@ -82,12 +85,13 @@ inline bool tc2_make_plan(const ModelDims& md, const std::vector<StepDesc>& step
   p->off_misc = o; o = al(o + kTcMiscBytes);
   p->off_bias = o; o = al(o + (2 * md.h + 64) * 4);       // b1 | b2 | b3 of the current pass
   p->off_tab = o;  o = al(o + 2 * 2 * kEpPad * 16);       // gather-order tables of the current and the next step
+  p->off_w3 = o;   o = al(o + 2 * kT2W3Bytes);            // last-layer weights of two pieces (their own double buffer)
   p->off_ring = o;
   const uint32_t limit = 227 * 1024;
   p->nst = std::min<int>(kT2MaxStages, (limit - o) / kT2StageBytes);
   p->smem_bytes = o + (size_t)p->nst * kT2StageBytes;
   p->tmem_cols = 512;
-  return p->nst >= 4;
+  return p->nst >= 3;
 }
 
 // Epilogue warp -> MMA warp handoff: every lane has fenced its own writes, one lane arrives for the warp.
@@ -170,8 +174,10 @@ __device__ __forceinline__ T2Geom t2_geom(int h) {
 //   L2        (chunk j, part p)  ring stage: 32 KB of chunk j's weights = one k-quarter of a 128-column chunk, or two
 //                                            k-quarters of a 64-column chunk; needs A1 quarters and a free slot
 //   L2_DONE   (chunk j)          MMA only  : commit -> epilogue
-//   L3        (piece j)          ring stage: last-layer k-slabs of piece j; waits for the packed piece, accumulates it
-enum { T2_OP_L1_STAGE = 0, T2_OP_L1, T2_OP_L2, T2_OP_L2_DONE, T2_OP_L3 };
+//   L3_STAGE  (piece j)          ring stage: last-layer k-slabs of piece j, taken (and held) one chunk before they are used:
+//                                            waiting for them at the point of use stalled the issuer for a TMA round trip
+//   L3        (piece j)          MMA only  : waits for the packed piece, accumulates it, releases the held stage
+enum { T2_OP_L1_STAGE = 0, T2_OP_L1, T2_OP_L2, T2_OP_L2_DONE, T2_OP_L3_STAGE, T2_OP_L3 };
 template <class F>
 __device__ __forceinline__ void t2_schedule(const T2Geom& g, F&& f) {
   f(T2_OP_L1_STAGE, 0, 0);
@@ -185,12 +191,15 @@ __device__ __forceinline__ void t2_schedule(const T2Geom& g, F&& f) {
   }
   f(T2_OP_L2_DONE, 0, 0);
   for (int j = 1; j < g.NJ; ++j) {
-    if (j >= 2) f(T2_OP_L3, j - 2, 0);                       // frees slot j & 1
+    if (j >= 2) f(T2_OP_L3, j - 2, 0);                       // frees slot j & 1 (and the piece's weight stage)
+    f(T2_OP_L3_STAGE, j - 1, 0);                             // weights of piece j - 1, a whole chunk before they are used
     const int parts = (g.cw(j) == 128) ? g.NQ : (g.NQ + 1) / 2;
     for (int p = 0; p < parts; ++p) f(T2_OP_L2, j, p);
     f(T2_OP_L2_DONE, j, 0);
   }
-  for (int j = (g.NJ >= 2 ? g.NJ - 2 : 0); j < g.NJ; ++j) f(T2_OP_L3, j, 0);
+  if (g.NJ >= 2) f(T2_OP_L3, g.NJ - 2, 0);
+  f(T2_OP_L3_STAGE, g.NJ - 1, 0);
+  f(T2_OP_L3, g.NJ - 1, 0);
 }
 
 // PROF: per-role cycle counters of CTA 0 (gbnf_get_profile).  A clock64() costs ~30 cycles on the latency-bound single-warp
@@ -225,6 +234,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
   float4* tab_s = reinterpret_cast<float4*>(smem + plan.off_tab);
   Tc2Misc* misc = reinterpret_cast<Tc2Misc*>(smem + plan.off_misc);
   unsigned char* ring = smem + plan.off_ring;
+  unsigned char* w3buf = smem + plan.off_w3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nst = plan.nst;
   const T2Geom G = t2_geom(md.h);
@@ -238,6 +248,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     for (int i = 0; i < 4; ++i) { ptx::mbar_init(&misc->a1r[i], 16); ptx::mbar_init(&misc->l1f[i], 1); }
     for (int i = 0; i < 3; ++i) { ptx::mbar_init(&misc->sr[i], 16); ptx::mbar_init(&misc->l2f[i], 1); }
     ptx::mbar_init(&misc->l3f, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&misc->w3full[i], 1); ptx::mbar_init(&misc->w3empty[i], 1); }
     ptx::fence_mbar_init();
     if (a.G_ll != nullptr) mixture_coefficients(a.rho, a.n_mix, a.skip_c, a.mix_mode, misc->coef);
   }
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================================
-    uint32_t sidx = 0, par = 0;
+    uint32_t sidx = 0, par = 0, ph_w3 = 0;
     int slot = 0;                                    // ring position kept incrementally: a runtime % or / costs ~100 cycles
     const long long p_t0 = T2_CLOCK();                // on this single latency-bound warp
     long long p_wait = 0;
@@ -292,8 +303,20 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                   const int q0 = 2 * y, nq = min(2, NQ - q0);
                   push(base + (size_t)(8 * q0) * 1024, (uint32_t)nq * 16384u); // two k-quarters: 16 slabs of 64 x 16
                 }
-              } else if (op == T2_OP_L3) {
-                push(w3 + (size_t)(G.ccol(x) >> 4) * np3 * 16, (uint32_t)((G.cw(x) >> 4) * np3) * 32u);
+              } else if (op == T2_OP_L3_STAGE) {
+                const int b = x & 1;
+                t2_wait(&misc->w3empty[b], ((ph_w3 >> b) & 1u) ^ 1u, a.error_flag, 11, lane);
+                ph_w3 ^= 1u << b;
+                if (ptx::elect_one()) {
+                  const uint32_t bytes = (uint32_t)((G.cw(x) >> 4) * np3) * 32u;
+                  if (a.exp_flags & 1) {
+                    ptx::mbar_arrive(&misc->w3full[b]);
+                  } else {
+                    ptx::mbar_arrive_expect_tx(&misc->w3full[b], bytes);
+                    ptx::tma_bulk_g2s(w3buf + (size_t)b * kT2W3Bytes, w3 + (size_t)(G.ccol(x) >> 4) * np3 * 16, bytes, &misc->w3full[b]);
+                  }
+                }
+                __syncwarp();
               }
             });
           }
@@ -310,6 +333,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     long long m_wa = 0, m_wf = 0, m_iss = 0, m_sr = 0, tw, ti;
     const uint64_t a0_desc = ptx::make_smem_desc(ptx::smem_u32(A0));
     const uint64_t ring_desc = ptx::make_smem_desc(ptx::smem_u32(ring));
+    const uint64_t w3_desc = ptx::make_smem_desc(ptx::smem_u32(w3buf));
+    uint32_t ph_w3f = 0;
     const uint32_t idesc_l1 = ptx::make_idesc_f16(128, kT2Chunk);
     const uint32_t idesc_l2 = ptx::make_idesc_f16(128, kT2Piece);
     int slot = 0;
@@ -406,8 +431,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 const uint64_t bd = stage_take();
                 const int cur_slot = slot;
                 if (x == 3) T2_TRACE(131 + 3 * (y & 1));
-                // The op after the LAST part of chunk x >= 1 is the last-layer piece x - 1: test its barrier and take its weight
-                // stage now, so that this bookkeeping overlaps with the MMAs issued below instead of idling the pipe.
+                // The op after the LAST part of chunk x >= 1 is the last-layer piece x - 1: test its barrier
+                // now, so that its latency overlaps with the MMAs issued below instead of idling the pipe.
                 const bool pre_l3 = (q0 + nq == NQ) && x >= 1;
                 if (pre_l3) {
                   const int sn = (x - 1) & 1;
@@ -436,11 +461,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                   if (q0 + nq == NQ) ptx::umma_commit(&misc->l2f[x & 1]);      // chunk complete -> epilogue
                 }
                 __syncwarp();
-                if (pre_l3) stage_prefetch();                                  // the piece's weights (queued MMAs hide this)
                 m_iss += T2_CLOCK() - ti;
                 if (x == 3) T2_TRACE(132 + 3 * (y & 1));
               } else if (op == T2_OP_L2_DONE) {
                 T2_TRACE(10 + x);
+              } else if (op == T2_OP_L3_STAGE) {
+                // producer-only op: the piece's weights go to their own buffer
               } else {
                 // last layer, k-piece x held packed in slot x & 1 (128-column chunk: 8 slabs at slot + 8 i; 64-column
                 // chunk: 4 slabs at slot + 16 i) -> last-layer accumulator
@@ -456,14 +482,17 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 m_sr += T2_CLOCK() - ti;
                 ph_sr ^= 1u << sl;
                 if (x == 1) T2_TRACE(137);
-                const uint64_t bd = stage_take();
+                ptx::mbar_wait(&misc->w3full[sl], (ph_w3f >> sl) & 1u, a.error_flag, 24);   // landed a chunk ago
+                ptx::tc_fence_after();
+                ph_w3f ^= 1u << sl;
+                const uint64_t bd = w3_desc + (uint64_t)((uint32_t)sl * (kT2W3Bytes >> 4));
                 if (ptx::elect_one()) {
                   const uint32_t at = tbase + G.slot_col[sl], d = tbase + G.la_col;
                   const uint32_t astep = (w == 128) ? 8u : 16u;
                   const int nsl = w >> 4;
                   for (int i = 0; i < nsl; ++i)
                     ptx::umma_f16_ts(d, at + astep * i, bd + (uint64_t)((uint32_t)i * b3_step), idesc_o, (x > 0 || i > 0) ? 1u : 0u);
-                  ptx::umma_commit(&misc->empty[slot]);
+                  ptx::umma_commit(&misc->w3empty[sl]);
                   if (x == NJ - 1) ptx::umma_commit(&misc->l3f);
                 }
                 __syncwarp();

@@ -189,6 +189,19 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
   for (int c = c0; c < c1; ++c)
     if (!h->packed[c]) return fail(GBNF_ERR_STATE, "component " + std::to_string(c) + " has not been packed");
   if (B == 0) return GBNF_OK;
+  // rows are independent: very large batches go through in slices, which bounds the per-launch scratch (mixture terms)
+  // and keeps the tile count inside an int
+  constexpr long long kMaxRowsPerLaunch = 1LL << 22;
+  if (B > kMaxRowsPerLaunch) {
+    for (long long r0 = 0; r0 < B; r0 += kMaxRowsPerLaunch) {
+      const long long nb = std::min(kMaxRowsPerLaunch, B - r0);
+      int rc = launch_coupling(h, x + r0 * h->md.D, nb, c0, c1, logq ? logq + r0 * ld_logq : nullptr, ld_logq,
+                               z_out ? z_out + r0 * h->md.D : nullptr, ldj_out ? ldj_out + r0 : nullptr, rho, n_mix, skip_c,
+                               mix_mode, G_ll ? G_ll + r0 : nullptr, st);
+      if (rc != GBNF_OK) return rc;
+    }
+    return GBNF_OK;
+  }
   CouplingArgs a{};
   a.x = x; a.B = B; a.c0 = c0; a.c1 = c1; a.logq = logq; a.ld_logq = ld_logq; a.z_out = z_out; a.ldj_out = ldj_out;
   a.rho = rho; a.n_mix = n_mix; a.skip_c = skip_c; a.mix_mode = mix_mode; a.G_ll = G_ll;
