@@ -185,15 +185,18 @@ __device__ __forceinline__ void t2_schedule(const T2Geom& g, F&& f) {
   if (g.NQ > 1) f(T2_OP_L1, 1, 0);
   // chunk 0 (always 128 wide: one part per k-quarter) is interleaved with the remaining layer-1 chunks, so that its part q is
   // issued as soon as A1 quarter q exists
+#pragma unroll
   for (int q = 0; q < g.NQ; ++q) {
     if (q + 2 < g.NQ) f(T2_OP_L1, q + 2, 0);
     f(T2_OP_L2, 0, q);
   }
   f(T2_OP_L2_DONE, 0, 0);
+#pragma unroll
   for (int j = 1; j < g.NJ; ++j) {
     if (j >= 2) f(T2_OP_L3, j - 2, 0);                       // frees slot j & 1 (and the piece's weight stage)
     f(T2_OP_L3_STAGE, j - 1, 0);                             // weights of piece j - 1, a whole chunk before they are used
     const int parts = (g.cw(j) == 128) ? g.NQ : (g.NQ + 1) / 2;
+#pragma unroll
     for (int p = 0; p < parts; ++p) f(T2_OP_L2, j, p);
     f(T2_OP_L2_DONE, j, 0);
   }
@@ -217,7 +220,11 @@ __device__ __forceinline__ void t2_stage_meta(const StepDesc* sd, int nnets, int
   m[0] = v0; m[1] = v1; m[2] = v2; m[3] = v3; m[4] = v4; m[5] = v5; m[6] = v6;
 }
 
-template <int TANH_MODE, int PROF>   // PROF: 0 production, 1 cycle counters + event trace, 2 event trace only (near-production timing)
+// PROF: 0 production, 1 cycle counters + event trace, 2 event trace only (near-production timing).
+// NQT: h / 128 as a compile-time constant (0 = read it from the model): with a constant geometry the whole schedule unrolls
+// into straight-line code, which matters on the MMA-issuer warp where every dependent scalar instruction costs 4-6 cycles
+// that are NOT hidden whenever a stage is issue-bound (measured ~400 cycles of bookkeeping per stage in the generic form).
+template <int TANH_MODE, int PROF, int NQT>
 __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArgs a, TcPlan plan) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // PTX predicate registers that carry the result of an early mbarrier.test_wait across the MMA block issued in between
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
   unsigned char* w3buf = smem + plan.off_w3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nst = plan.nst;
-  const T2Geom G = t2_geom(md.h);
+  const T2Geom G = t2_geom(NQT ? NQT * kT2Chunk : md.h);
   const int NQ = G.NQ;                     // layer-1 chunks = k-quarters of layer 2
   const int NJ = G.NJ;                     // layer-2 chunks = k-pieces of the last layer
   const int hs = md.h >> 4;                // k-slabs of the h x h layer
@@ -831,20 +838,25 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
 #undef T2_CLOCK
 #undef T2_TRACE
 
+template <int T, int P, int Q>
+inline cudaError_t tc2_configure_one() {
+  return cudaFuncSetAttribute(coupling_tc2_kernel<T, P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
 inline cudaError_t tc2_configure() {
-  cudaError_t e = cudaFuncSetAttribute(coupling_tc2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc2_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaSuccess;
+#define T2_CFG(T, P, Q) if (e == cudaSuccess) e = tc2_configure_one<T, P, Q>()
+  T2_CFG(0, 0, 0); T2_CFG(1, 0, 0); T2_CFG(0, 1, 0); T2_CFG(1, 1, 0); T2_CFG(0, 2, 0); T2_CFG(1, 2, 0);
+  T2_CFG(0, 0, 4); T2_CFG(1, 0, 4); T2_CFG(0, 1, 4); T2_CFG(1, 1, 4); T2_CFG(0, 2, 4); T2_CFG(1, 2, 4);
+#undef T2_CFG
   return e;
 }
 
 inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStream_t st, int prof) {
-#define T2_GO(T, P) coupling_tc2_kernel<T, P><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p)
-  if (p.tanh_mode == 0) { if (prof == 1) T2_GO(0, 1); else if (prof == 2) T2_GO(0, 2); else T2_GO(0, 0); }
-  else                  { if (prof == 1) T2_GO(1, 1); else if (prof == 2) T2_GO(1, 2); else T2_GO(1, 0); }
+#define T2_GO(T, P, Q) coupling_tc2_kernel<T, P, Q><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p)
+#define T2_GO_Q(T, P) do { if (a.md.h == 512) T2_GO(T, P, 4); else T2_GO(T, P, 0); } while (0)
+  if (p.tanh_mode == 0) { if (prof == 1) T2_GO_Q(0, 1); else if (prof == 2) T2_GO_Q(0, 2); else T2_GO_Q(0, 0); }
+  else                  { if (prof == 1) T2_GO_Q(1, 1); else if (prof == 2) T2_GO_Q(1, 2); else T2_GO_Q(1, 0); }
+#undef T2_GO_Q
 #undef T2_GO
   return 0;
 }
