@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = (v[e] + t[e].x) * t[e].y + t[e].z;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) zrow[__float_as_int(t[e].w)] = v[e];
+              for (int e = 0; e < 8; ++e) if (ch * 8 + e < in_dim) zrow[__float_as_int(t[e].w)] = v[e];   // never write the scratch column
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = (ch * 8 + e < in_dim) ? v[e] : 0.f;
               st_shared_v4(A0 + a_chunk_off(row, ch * 8), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                   lsum += (j < out_dim) ? __logf(s) : 0.f;                              // glow.py:338
                 }
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) zrow[__float_as_int(t[jj].w)] = z[jj];
+                for (int jj = 0; jj < 8; ++jj) if (g * 8 + jj < out_dim) zrow[__float_as_int(t[jj].w)] = z[jj];
               } else {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                   }
                   if (md.kind == GBNF_KIND_GLOW || net == 1) {
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) zrow[__float_as_int(t[jj].w)] = z[jj];
+                    for (int jj = 0; jj < 8; ++jj) if (c0 + half * 8 + jj < out_dim) zrow[__float_as_int(t[jj].w)] = z[jj];
                   }
                 }
               }
