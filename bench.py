@@ -209,6 +209,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line unless the caller asks for more
         dist.init_process_group("nccl", device_id=device)
     cfg = CONFIGS[a.config]
     C, D = cfg["C"], cfg["D"]
