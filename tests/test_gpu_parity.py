@@ -320,3 +320,22 @@ def test_repack_after_parameter_update():
         assert rel_err(b.cpu().numpy()[:, 0], orc.component_logq(md2, x, 0)) < 1e-5
     finally:
         model.release()
+
+
+def test_very_large_batch_is_sliced():
+    """Batches above 2^22 rows go through the coupling kernel in slices (bounded scratch); per-row results must not depend on
+    where the slice boundaries fall."""
+    md = orc.make_synthetic_model("realnvp", 2, 2, 1, 128, seed=11)
+    model = build_model(md, "cuda", gemm_mode="f16fast")
+    try:
+        B = (1 << 22) + 1000
+        x = torch.randn((B, 2), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+        G = model.mixture_log_density(x, 2)
+        assert torch.isfinite(G).all()
+        for a, b in ((0, 300), ((1 << 22) - 150, (1 << 22) + 150), (B - 257, B)):
+            assert torch.equal(model.mixture_log_density(x[a:b].contiguous(), 2), G[a:b])
+        lq = model.component_log_density(x[(1 << 22) - 64:(1 << 22) + 64].contiguous()).cpu().numpy()
+        ref = orc.all_component_logq(orc.cast_model(md, np.float64), x[(1 << 22) - 64:(1 << 22) + 64].cpu().numpy().astype(np.float64))
+        close(lq, ref, "f16fast", "realnvp")
+    finally:
+        model.release()
