@@ -339,3 +339,43 @@ def test_very_large_batch_is_sliced():
         close(lq, ref, "f16fast", "realnvp")
     finally:
         model.release()
+
+
+# ---- every code path of the PIPELINED tensor-core kernel against the oracle (the golden fixtures with these variants have
+#      h = 64 and therefore run the serial kernel): additive coupling, ReLU / mixed nets, toy base density, odd and maximal D,
+#      every hidden width (h = 128 .. 512: one to four layer-1 chunks, both TMEM geometries) ------------------------------------
+PIPELINED_VARIANTS = {
+    "glow_additive_relu_h128": dict(kind="glow", D=6, C=2, K=3, h=128, coupling="additive", act="relu"),
+    "glow_additive_h256": dict(kind="glow", D=7, C=2, K=2, h=256, coupling="additive"),
+    "glow_affine_d64_h384": dict(kind="glow", D=64, C=2, K=2, h=384),
+    "glow_affine_d63_h512": dict(kind="glow", D=63, C=2, K=3, h=512),
+    "glow_affine_d2_h128": dict(kind="glow", D=2, C=3, K=2, h=128),
+    "realnvp_mixed_d5_h128": dict(kind="realnvp", D=5, C=3, K=4, h=128, act="mixed"),
+    "realnvp_bn_d9_h384": dict(kind="realnvp", D=9, C=2, K=3, h=384, batch_norm=True),
+    "realnvp_toy_d2_h512": dict(kind="realnvp", D=2, C=3, K=2, h=512, rho_init="uniform", toy_base=True),
+}
+
+
+@pytest.mark.parametrize("mode", ["f16", "f16fast"])
+@pytest.mark.parametrize("name", list(PIPELINED_VARIANTS))
+def test_pipelined_kernel_variants_vs_oracle(name, mode):
+    kw = dict(PIPELINED_VARIANTS[name])
+    md = orc.make_synthetic_model(kw.pop("kind"), kw.pop("D"), kw.pop("C"), kw.pop("K"), kw.pop("h"), seed=21, **kw)
+    B = 517                                                          # four full tiles + a ragged one
+    x = np.random.default_rng(77).standard_normal((B, md["D"])).astype(np.float32)
+    model = build_model(md, "cuda", gemm_mode=mode)
+    try:
+        assert model.info()["pipelined"] == 1
+        ref64 = orc.all_component_logq(orc.cast_model(md, np.float64), x.astype(np.float64))
+        G, lq = model.mixture_log_density(dev(x), md["C"], return_logq=True)
+        # low-dimensional models have |log q| of a few units: relative gate + the f16 absolute term of their family
+        close(lq.cpu().numpy(), ref64, mode, "realnvp" if md["D"] < 16 else md["kind"])
+        Gref = orc.mixture_recursion(ref64, md["rho"].astype(np.float64), md["C"])
+        close(G.cpu().numpy(), Gref, mode, "realnvp" if md["D"] < 16 else md["kind"])
+        # the 5-tuple (z, ldj) of one component through the same kernel
+        z, ldj = model.component_forward(dev(x), md["C"] - 1)
+        zr, ldjr = orc.component_forward(orc.cast_model(md, np.float64), x.astype(np.float64), md["C"] - 1)
+        np.testing.assert_allclose(z.cpu().numpy(), zr, rtol=2e-2, atol=2e-2)
+        np.testing.assert_allclose(ldj.cpu().numpy(), ldjr, rtol=2e-2, atol=2e-2)
+    finally:
+        model.release()
