@@ -605,6 +605,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             ptx::tc_fence_before();
             t2_warp_arrive(&misc->a0r, lane);
             if (tr) T2_TRACE(40 + 40 * (g & 1));
+            if (PROF && tr && g == 0 && a.prof != nullptr && blockIdx.x == 0 && units == kT2TraceUnit + 1 && lane == 0) a.prof[32 + 200] = clock64();
             // ---- stage this pass's biases (b1 | b2 | b3 are contiguous in fblob) and the next step's tables in shared
             //      memory while the MMA warp issues layer 1: a first-touch global load in the chunk epilogues would stall
             //      all four warps of a scheduler at once for an L2 round trip ----

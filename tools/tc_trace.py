@@ -49,5 +49,7 @@ names[138] = "MMA* layer-1 weight stage taken"
 ev = sorted((v, names[i]) for i, v in enumerate(t) if v > 0 and i in names)
 t0 = ev[0][0]
 print(f"{cfg_name} {mode}: one coupling pass of CTA 0 (cycles relative to first event)")
+if t[200] > 0 and t[40] > 0:
+    print(f"PASS LENGTH (a0r arrival of this pass -> a0r arrival of the next): {t[200] - t[40]} cycles")
 for v, n in ev:
     print(f"{v - t0:8d}  {n}")
