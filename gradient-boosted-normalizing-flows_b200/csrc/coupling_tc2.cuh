@@ -50,12 +50,14 @@ struct Tc2Misc {
   uint32_t tmem_base;
   uint32_t last_flag;
   int meta[2][8];     // per step (double buffered): in_dim, out_dim, Kp of layer 1, Np of the last layer (net 0, 1), bias offsets
+                      // (net 0, 1), offset of the gather-order tables (t2_stage_meta)
   float coef[kMaxComponents];
-  float part[3 * kTcRows];
-  float part2[3 * kTcRows];
 };
 
-static_assert(sizeof(Tc2Misc) <= kTcMiscBytes, "misc region too small");
+constexpr uint32_t kT2MiscBytes = 1536;
+static_assert(sizeof(Tc2Misc) <= kT2MiscBytes, "misc region too small");
+
+__host__ __device__ inline uint32_t t2_bias_stride(int h) { return (uint32_t)(2 * h + 64); }   // floats per bias buffer
 
 // Eligibility of a configuration for the pipelined kernel (host).
 inline bool tc2_eligible(const ModelDims& md, const std::vector<StepDesc>& steps) {
@@ -79,11 +81,11 @@ inline bool tc2_make_plan(const ModelDims& md, const std::vector<StepDesc>& step
   p->K0p = k0p; p->out_max = out_max;
   uint32_t o = 0;
   p->off_zs = o;   o = al(o + kTcRows * md.Dv * 4);
-  p->off_a0 = o;   o = al(o + (k0p / 16) * 4096);
+  p->off_a0 = o;   o = al(o + (k0p / 16) * 4096);        // also hosts the per-row partial sums at the end of a component (6 x 128 floats)
   p->off_a1 = o;   o = al(o + kTcRows * md.D * 4);       // here: the untransformed x tile (reloaded into zs per component)
   p->off_sh = o;   o = al(o + (md.nnets == 2 ? kTcRows * out_max * 4 : 0));
-  p->off_misc = o; o = al(o + kTcMiscBytes);
-  p->off_bias = o; o = al(o + (2 * md.h + 64) * 4);       // b1 | b2 | b3 of the current pass
+  p->off_misc = o; o = al(o + kT2MiscBytes);
+  p->off_bias = o; o = al(o + 2 * t2_bias_stride(md.h) * 4);   // b1 | b2 | b3 of the current and of the next pass
   p->off_tab = o;  o = al(o + 2 * 2 * kEpPad * 16);       // gather-order tables of the current and the next step
   p->off_w3 = o;   o = al(o + 2 * kT2W3Bytes);            // last-layer weights of two pieces (their own double buffer)
   p->off_ring = o;
@@ -217,7 +219,28 @@ __device__ __forceinline__ void t2_stage_meta(const StepDesc* sd, int nnets, int
   const int v3 = __ldg(&sd->layer[0][2].Np), v5 = (int)__ldg(&sd->layer[0][0].b_off);
   int v4 = 0, v6 = 0;
   if (nnets == 2) { v4 = __ldg(&sd->layer[1][2].Np); v6 = (int)__ldg(&sd->layer[1][0].b_off); }
-  m[0] = v0; m[1] = v1; m[2] = v2; m[3] = v3; m[4] = v4; m[5] = v5; m[6] = v6;
+  m[0] = v0; m[1] = v1; m[2] = v2; m[3] = v3; m[4] = v4; m[5] = v5; m[6] = v6; m[7] = (int)__ldg(&sd->ep_off);
+}
+// The same copy without stalling anybody: threads i = 0..7 each issue one 4-byte cp.async (the low words of the 64-bit
+// offsets); the values are visible after the issuing threads' cp.async.wait_all and a CTA barrier.
+__device__ __forceinline__ void t2_stage_meta_async(const StepDesc* sd, int nnets, int* m, int i) {
+  const void* src = nullptr;
+  switch (i) {
+    case 0: src = &sd->in_dim; break;
+    case 1: src = &sd->out_dim; break;
+    case 2: src = &sd->layer[0][0].Kp; break;
+    case 3: src = &sd->layer[0][2].Np; break;
+    case 4: if (nnets == 2) src = &sd->layer[1][2].Np; break;
+    case 5: src = &sd->layer[0][0].b_off; break;
+    case 6: if (nnets == 2) src = &sd->layer[1][0].b_off; break;
+    case 7: src = &sd->ep_off; break;
+    default: break;
+  }
+  if (src != nullptr) ptx::cp_async4(m + i, src);
+}
+// b1 | b2 | b3 of one coupling pass (contiguous in fblob, 16-byte aligned) -> a bias buffer, asynchronously
+__device__ __forceinline__ void t2_stage_bias_async(float* dst, const float* src, int nfloat, int et) {
+  for (int i = et; i < (nfloat >> 2); i += kT2EpiThreads) ptx::cp_async16(dst + 4 * i, src + 4 * i);
 }
 
 // PROF: 0 production, 1 cycle counters + event trace, 2 event trace only (near-production timing).
@@ -513,11 +536,17 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     const int h0col = min(D, g * dq), h1col = min(D, (g + 1) * dq);   // column split for elementwise passes
     uint32_t units = 0, stepc = 0;
     uint32_t ph_l2f = 0;
-    // the first step's gather-order tables; afterwards every step stages the tables of the one that follows it
-    if (blockIdx.x < a.num_units && et < 2 * kEpPad) {
+    float* const part = reinterpret_cast<float*>(A0);   // per-row partial sums of a component's log-density (A0 is dead by then)
+    float* const part2 = part + 3 * kTcRows;
+    const uint32_t bstride = t2_bias_stride(md.h);
+    // the first step's gather-order tables, scalars and biases; afterwards every pass stages what the next one needs
+    // (cp.async issued while this pass waits for the tensor core, completed and published at the end of the pass)
+    if (blockIdx.x < a.num_units) {
       const int cb0 = a.c0 + ((int)blockIdx.x % a.split) * a.comps_per_unit;
-      tab_s[et] = __ldg(reinterpret_cast<const float4*>(a.fblob + a.steps[cb0 * md.K].ep_off) + et);
-      if (et == 0) t2_stage_meta(a.steps + cb0 * md.K, md.nnets, misc->meta[0]);
+      const StepDesc* sd0 = a.steps + cb0 * md.K;
+      if (et < 2 * kEpPad) ptx::cp_async16(tab_s + et, reinterpret_cast<const float4*>(a.fblob + __ldg(&sd0->ep_off)) + et);
+      if (et == 0) t2_stage_meta(sd0, md.nnets, misc->meta[0]);
+      t2_stage_bias_async(bias_s, a.fblob + __ldg(&sd0->layer[0][0].b_off), 2 * md.h + __ldg(&sd0->layer[0][2].Np), et);
     }
     const bool tr = (warp_e & 3) == 0;     // one tracing warp per group
     const long long e_t0 = T2_CLOCK();
@@ -555,11 +584,13 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           for (int i = et; i < total; i += kT2EpiThreads) { const int r = i / D; zs[r * Dv + (i - r * D)] = xs[i]; }
           if (g == 0) for (int p = D; p < Dv; ++p) zrow[p] = 0.f;         // scratch column(s): target of padded table entries
         }
+        ptx::cp_async_wait_all();                    // (first component of the launch: the prologue's staging copies)
         t2_epi_bar();
         e_x += T2_CLOCK() - e_tmp;
         float lsum = 0.f;                            // this thread's share of the data-dependent log-det
         for (int k = 0; k < md.K; ++k, ++stepc) {
           e_tmp = T2_CLOCK();
+          if (tr) T2_TRACE(72 + 40 * (g & 1));
           const StepDesc* sd = a.steps + (c * md.K + k);
           const int* meta = misc->meta[stepc & 1u];                          // staged a step ahead
           const int out_dim = meta[1], in_dim = meta[0];
@@ -594,10 +625,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             }
           }
           e_pro += T2_CLOCK() - e_tmp;
+          if (tr) T2_TRACE(73 + 40 * (g & 1));
           for (int net = 0; net < md.nnets; ++net, ++units) {
             const int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
-            const float* b1 = bias_s + g * 32;
-            const float* bias = bias_s + 2 * md.h;
+            const float* bias_c = bias_s + (units & 1u) * bstride;           // staged by the previous pass
+            const float* b1 = bias_c + g * 32;
+            const float* bias = bias_c + 2 * md.h;
             const uint32_t upar = units & 1u;
             const int np3 = meta[3 + net];
             // hand A0 (and every drained TMEM region) to the MMA warp
@@ -606,21 +639,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             t2_warp_arrive(&misc->a0r, lane);
             if (tr) T2_TRACE(40 + 40 * (g & 1));
             if (PROF && tr && g == 0 && a.prof != nullptr && blockIdx.x == 0 && units == kT2TraceUnit + 1 && lane == 0) a.prof[32 + 200] = clock64();
-            // ---- stage this pass's biases (b1 | b2 | b3 are contiguous in fblob) and the next step's tables in shared
-            //      memory while the MMA warp issues layer 1: a first-touch global load in the chunk epilogues would stall
-            //      all four warps of a scheduler at once for an L2 round trip ----
-            t2_epi_bar();                              // nobody still reads the previous pass's biases
-            {
-              const float4* bsrc = reinterpret_cast<const float4*>(a.fblob + meta[5 + net]);
-              const int nb4 = (2 * md.h + np3) >> 2;
-              for (int i = et; i < nb4; i += kT2EpiThreads) reinterpret_cast<float4*>(bias_s)[i] = __ldg(bsrc + i);
-              if (net == 0 && sd_next != nullptr && et >= kT2EpiThreads - 2 * kEpPad) {
-                const int i = et - (kT2EpiThreads - 2 * kEpPad);
-                tab_s[((stepc + 1) & 1u) * (2 * kEpPad) + i] = __ldg(reinterpret_cast<const float4*>(a.fblob + __ldg(&sd_next->ep_off)) + i);
-              }
-              if (net == 0 && sd_next != nullptr && et == 0) t2_stage_meta(sd_next, md.nnets, misc->meta[(stepc + 1) & 1u]);
-            }
-            t2_epi_bar();
+            // ---- staging for the NEXT pass, entirely off the critical path (a first-touch global load here, or in the
+            //      chunk epilogues, would stall all four warps of a scheduler for an L2 round trip): the next step's scalars
+            //      now; its tables and the next pass's biases once those scalars are visible (after layer 1, below) ----
+            if (net == 0 && sd_next != nullptr && et < 8) t2_stage_meta_async(sd_next, md.nnets, misc->meta[(stepc + 1) & 1u], et);
             // ---- layer 1: chunk q in L1 slot q & 1 (128 columns, 32 per thread) -> act -> fp16 pairs written to the A1
             //      region [64 q, 64 q + 64) (normally a different TMEM region; see T2Geom::l1_even_inplace) ----
             for (int q = 0; q < NQ; ++q) {
@@ -646,6 +668,20 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               if (tr) T2_TRACE(45 + 40 * (g & 1) + q);
               e_l1 += T2_CLOCK() - e_tmp;
             }
+            // the epilogue now idles until layer-2 chunk 0 completes: publish the next step's scalars and start the copies
+            // that depend on them (biases b1 | b2 | b3 of the next pass are contiguous in fblob)
+            ptx::cp_async_wait_all();
+            t2_epi_bar();
+            if (net + 1 < md.nnets) {
+              t2_stage_bias_async(bias_s + ((units + 1) & 1u) * bstride, a.fblob + meta[5 + net + 1], 2 * md.h + meta[3 + net + 1], et);
+            } else if (sd_next != nullptr) {
+              const int* mn = misc->meta[(stepc + 1) & 1u];
+              t2_stage_bias_async(bias_s + ((units + 1) & 1u) * bstride, a.fblob + mn[5], 2 * md.h + mn[3], et);
+              if (et >= kT2EpiThreads - 2 * kEpPad) {
+                const int i = et - (kT2EpiThreads - 2 * kEpPad);
+                ptx::cp_async16(tab_s + ((stepc + 1) & 1u) * (2 * kEpPad) + i, reinterpret_cast<const float4*>(a.fblob + mn[7]) + i);
+              }
+            }
             // ---- layer 2: chunk j in slot j & 1 -> act -> fp16 pairs packed in place = k-piece j of the last layer's A
             //      operand.  128-column chunk: 32 columns per thread compacted into slot[0:64) (the quadrant's four warps
             //      synchronise between reading and overwriting); 64-column chunk: 16 columns per thread packed into the first
@@ -660,7 +696,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               ptx::tc_fence_after();
               e_tmp = T2_CLOCK();
               const uint32_t sc = lane_base + G.slot_col[sl];
-              const float* bj = bias_s + md.h + G.ccol(j);
+              const float* bj = bias_c + md.h + G.ccol(j);
               if (G.cw(j) == 128) {
                 uint32_t p[16];
                 {
@@ -755,7 +791,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 }
               }
             }
-            if (net == md.nnets - 1) t2_quad_bar(quad);   // z2 updates visible to the row's other threads before the next gather
+            // z2 updates visible to the row's other threads, and the staged biases / tables / scalars of the next pass to
+            // everybody, before the next gather
+            ptx::cp_async_wait_all();
+            t2_epi_bar();
             if (tr) T2_TRACE(71 + 40 * (g & 1));
             e_l3 += T2_CLOCK() - e_tmp;
           }
@@ -766,11 +805,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
         const float* bi = bm + Dv;
         float q = 0.f;
         for (int p = h0col; p < h1col; ++p) { const float d = zrow[p] - __ldg(bm + p); q = fmaf(d * d, __ldg(bi + p), q); }
-        if (g > 0) { misc->part[(g - 1) * kTcRows + row] = q; misc->part2[(g - 1) * kTcRows + row] = lsum; }
+        if (g > 0) { part[(g - 1) * kTcRows + row] = q; part2[(g - 1) * kTcRows + row] = lsum; }
         t2_quad_bar(quad);
         if (g == 0) {
-          q += misc->part[row] + misc->part[kTcRows + row] + misc->part[2 * kTcRows + row];
-          const float ldj_tot = (lsum + misc->part2[row] + misc->part2[kTcRows + row] + misc->part2[2 * kTcRows + row]) +
+          q += part[row] + part[kTcRows + row] + part[2 * kTcRows + row];
+          const float ldj_tot = (lsum + part2[row] + part2[kTcRows + row] + part2[2 * kTcRows + row]) +
                                 __ldg(a.fblob + cd.const_off);
           const float lq = (__ldg(bm + 2 * Dv) - q) + ldj_tot;
           if (gr < a.B) {
