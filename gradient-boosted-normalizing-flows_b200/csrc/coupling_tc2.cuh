@@ -591,6 +591,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
         for (int k = 0; k < md.K; ++k, ++stepc) {
           e_tmp = T2_CLOCK();
           if (tr) T2_TRACE(72 + 40 * (g & 1));
+          if (PROF && tr && g == 0 && a.prof != nullptr && blockIdx.x == 0 && units == kT2TraceUnit + 1 && lane == 0) a.prof[32 + 201] = clock64();
           const StepDesc* sd = a.steps + (c * md.K + k);
           const int* meta = misc->meta[stepc & 1u];                          // staged a step ahead
           const int out_dim = meta[1], in_dim = meta[0];
@@ -657,12 +658,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 uint32_t r[32];
                 ptx::tmem_ld32(lane_base + G.l1_col[q & 1] + (uint32_t)g * 32u, r);
                 ptx::tmem_ld_wait();
+                if (PROF && warp_e == 0 && q == 1) T2_TRACE(120);
                 if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, b1 + q * kT2Chunk, p);
                 else               t2_act_pack32<2, TANH_MODE>(r, b1 + q * kT2Chunk, p);
+                if (PROF && warp_e == 0 && q == 1) T2_TRACE(121);
               }
               if (G.l1_even_inplace && !(q & 1)) t2_quad_bar(quad);   // packed quarter may overlap the row's unread accumulator
               ptx::tmem_st16(lane_base + (uint32_t)q * 64u + (uint32_t)g * 16u, p);
               ptx::tmem_st_wait();
+              if (PROF && warp_e == 0 && q == 1) T2_TRACE(122);
               ptx::tc_fence_before();
               t2_warp_arrive(&misc->a1r[q], lane);
               if (tr) T2_TRACE(45 + 40 * (g & 1) + q);
@@ -793,9 +797,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             }
             // z2 updates visible to the row's other threads, and the staged biases / tables / scalars of the next pass to
             // everybody, before the next gather
+            if (tr) T2_TRACE(71 + 40 * (g & 1));
             ptx::cp_async_wait_all();
             t2_epi_bar();
-            if (tr) T2_TRACE(71 + 40 * (g & 1));
+            if (tr) T2_TRACE(74 + 40 * (g & 1));
             e_l3 += T2_CLOCK() - e_tmp;
           }
         }

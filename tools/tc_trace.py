@@ -42,7 +42,9 @@ for g in (0, 1):
         names[b + 10 + j] = f"EPI{g} l2f chunk {j} seen"; names[b + 20 + j] = f"EPI{g} sr chunk {j} arrived"
     names[b + 30] = f"EPI{g} l3f seen"; names[b + 31] = f"EPI{g} last-layer epilogue done"
     names[b + 32] = f"EPI{g} pass top"; names[b + 33] = f"EPI{g} gather loop done"
-for i, n in enumerate(["L1 chunk 1: barrier seen", "tcgen05.ld done", "bias+act+pack done", "quad barrier passed", "tcgen05.st done", "arrived"]):
+    names[b + 34] = f"EPI{g} end-of-pass barrier passed"
+names[201] = "EPI0 NEXT pass top"; names[200] = "EPI0 NEXT pass a0r arrived"
+for i, n in enumerate(["L1 chunk 1: tcgen05.ld done", "L1 chunk 1: bias+act+pack done", "L1 chunk 1: tcgen05.st done"]):
     names[120 + i] = "EPI0-w0 " + n
 for i, n in enumerate(["L2(4,h0) op start", "L2(4,h0) stage acquired", "L2(4,h0) 16 MMA issued", "L2(4,h1) op start", "L2(4,h1) stage acquired", "L2(4,h1) 16 MMA issued", "L3(1) op start", "L3(1) piece barrier passed"]):
     names[130 + i] = "MMA* " + n
