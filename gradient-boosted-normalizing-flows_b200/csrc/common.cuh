@@ -22,7 +22,7 @@ constexpr int kEpPad = 64;             // padded length of the gather-order step
 struct LayerDesc {
   int K_in, N_out, Kp, Np;
   int NC, NC2;       // N-chunk width of the f16 image (== Np for the single-chunk layout); NC2 != 0: width of the odd
-                     // chunks (chunk widths alternate NC, NC2, NC, ...; the current kernels use uniform chunks, NC2 = 0)
+                     // chunks (chunk widths alternate NC, NC2, NC, ...: h = 512 in the pipelined kernel uses 128 / 64)
   long long w_off;   // element offset into wblob (float for fp32, __half for f16)
   long long b_off;   // float offset into fblob; Np entries, zero padded
 };

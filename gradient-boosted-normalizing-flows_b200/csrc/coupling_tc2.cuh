@@ -28,6 +28,7 @@
 namespace gbnf {
 
 constexpr int kT2Chunk = 128;        // layer-1 chunk = k-quarter of layer 2 = wide layer-2 chunk
+constexpr int kT2Piece = 64;         // narrow layer-2 chunk (h = 512 only)
 constexpr int kT2Threads = 576;       // 2 control warps + 16 epilogue warps
 constexpr int kT2EpiThreads = 512;
 constexpr int kT2MaxStages = 8;
@@ -43,8 +44,7 @@ struct Tc2Misc {
   uint64_t sr[3];     // epilogue -> MMA : A2 piece stored in hole i, its accumulator drained                  (4 arrivals)
   uint64_t l1f[4];    // MMA -> epilogue : layer-1 chunk q accumulated        (tcgen05.commit)
   uint64_t l2f[3];    // MMA -> epilogue : layer-2 chunk in hole i accumulated
-  uint64_t l3p[2];    // MMA -> epilogue : last-layer product of the piece in slot i written (tcgen05.commit)
-  uint64_t sfree[2];  // epilogue -> MMA : that product has been read, slot i may be overwritten by chunk j + 2    (16 arrivals)
+  uint64_t l3f;       // MMA -> epilogue : last layer accumulated
   uint64_t w3full[2]; // producer -> MMA : last-layer weights of a piece landed in their own double buffer (outside the ring)
   uint64_t w3empty[2];// MMA -> producer : that buffer may be refilled
   uint32_t tmem_base;
@@ -111,6 +111,18 @@ __device__ __forceinline__ void t2_wait(uint64_t* bar, uint32_t parity, int* err
 __device__ __forceinline__ void t2_quad_bar(int quad) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory"); }
 __device__ __forceinline__ void t2_epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
+// 16 accumulator values of one row -> bias + activation -> 8 packed fp16 pairs
+template <int ACT, int TANH_MODE>
+__device__ __forceinline__ void t2_act_pack16(const uint32_t (&r)[16], const float* __restrict__ bias, uint32_t* p) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);      // staged in shared memory (broadcast read)
+    p[2 * q + 0] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 0]) + b.x),
+                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 1]) + b.y));
+    p[2 * q + 1] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 2]) + b.z),
+                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 3]) + b.w));
+  }
+}
 // 32 accumulator values of one row -> bias + activation -> 16 packed fp16 pairs
 template <int ACT, int TANH_MODE>
 __device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const float* __restrict__ bias, uint32_t* p) {
@@ -126,28 +138,28 @@ __device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const flo
 
 
 // ---- TMEM geometry ---------------------------------------------------------------------------------------------
-// A1 (layer-2 A operand, fp16 pairs) occupies columns [0, h/2): k-quarter q at [64 q, 64 q + 64).  Two 128-column accumulator
-// slots follow (at h = 512 they fill TMEM exactly); layer-2 chunk j (128 columns) lives in slot j & 1, layer-1 chunk q in L1
-// slot q & 1.  128-column accumulators matter: under sustained load an N = 64 MMA costs ~75 cycles, an N = 128 MMA ~97.
-// There is NO persistent last-layer accumulator: the last layer's product with k-piece j is written (not accumulated) into
-// the upper half of slot j & 1, which the in-place packing of the piece has just vacated, and the epilogue sums the pieces'
-// partial results in registers.
+// A1 (layer-2 A operand, fp16 pairs) occupies columns [0, h/2): k-quarter q at [64 q, 64 q + 64).  Two accumulator slots
+// follow; layer-2 chunk j lives in slot j & 1, layer-1 chunk q in L1 slot q & 1 (always 128 wide).  h = 512 leaves only
+// 256 columns: slot 0 = 128, slot 1 = 64, last-layer accumulator = 64, and layer 2 is cut into chunks of 128/64/128/64/128
+// columns; narrower models use two 128-column slots.  128-column accumulators matter because a tcgen05.mma costs ~44 cycles
+// to issue (blocking issue + descriptor arithmetic) but an N=64 MMA executes in 32: only N=128 keeps the pipe busy.
 struct T2Geom {
   int NQ, NJ;
-  bool tight;           // h = 512: A1 + the two accumulator slots fill all 512 columns
+  bool tight;
   bool l1_in_slot0;     // layer-1 accumulators share accumulator slot 0 (then layer-2 chunk 0 must wait for them to drain)
   bool l1_even_inplace; // the even layer-1 chunks accumulate inside the A1 region they are packed into
-  uint32_t slot_col[2], l1_col[2];
-  __device__ __forceinline__ int cw(int) const { return 128; }
-  __device__ __forceinline__ int ccol(int j) const { return 128 * j; }
+  uint32_t slot_col[2], l1_col[2], la_col;
+  __device__ __forceinline__ int cw(int j) const { return (tight && (j & 1)) ? 64 : 128; }
+  __device__ __forceinline__ int ccol(int j) const { return tight ? 192 * (j >> 1) + ((j & 1) ? 128 : 0) : 128 * j; }
 };
 __device__ __forceinline__ T2Geom t2_geom(int h) {
   T2Geom g;
   g.NQ = h / kT2Chunk;
   g.tight = (h == 512);
-  g.NJ = g.NQ;
+  g.NJ = g.tight ? 5 : g.NQ;
   const uint32_t a1w = (uint32_t)h >> 1;
   g.slot_col[0] = a1w; g.slot_col[1] = a1w + 128u;
+  g.la_col = g.tight ? 448u : a1w + 256u;
   // Layer-1 accumulators (128 columns each, two in flight).  Keeping them OUT of slot 0 lets layer-2 chunk 0 start as soon as
   // the first A1 quarter exists.  h = 512: even chunks use the upper half of the A1 region itself ([128, 256): still unused
   // when chunk 0 accumulates, packed in place by chunk 2), odd chunks use slot 1 + the last-layer accumulator ([384, 512)).
@@ -161,12 +173,13 @@ __device__ __forceinline__ T2Geom t2_geom(int h) {
 // ---- the fixed per-pass schedule, walked identically by the TMA producer and the MMA issuer ------------------------
 //   L1_STAGE  ()                 ring stage: W1 of all layer-1 chunks (held while the chunks are issued)
 //   L1        (chunk q)          MMA only  : A0 x W1 chunk q -> L1 slot q & 1 (chunks >= 2 wait for the slot to be drained)
-//   L2        (chunk j, part p)  ring stage: 32 KB of chunk j's weights = one k-quarter; needs A1 quarters and a free slot
+//   L2        (chunk j, part p)  ring stage: 32 KB of chunk j's weights = one k-quarter of a 128-column chunk, or two
+//                                            k-quarters of a 64-column chunk; needs A1 quarters and a free slot
 //   L2_DONE   (chunk j)          MMA only  : commit -> epilogue
-//   L3_STAGE  (piece j)          producer  : last-layer k-slabs of piece j -> their own double buffer, a chunk before they are used
-//   L3        (piece j)          MMA only  : waits for the packed piece, writes its last-layer product into the slot's upper half
+//   L3_STAGE  (piece j)          ring stage: last-layer k-slabs of piece j, taken (and held) one chunk before they are used:
+//                                            waiting for them at the point of use stalled the issuer for a TMA round trip
+//   L3        (piece j)          MMA only  : waits for the packed piece, accumulates it, releases the held stage
 enum { T2_OP_L1_STAGE = 0, T2_OP_L1, T2_OP_L2, T2_OP_L2_DONE, T2_OP_L3_STAGE, T2_OP_L3 };
-__host__ __device__ constexpr int t2_l3_pos(int nq) { return nq > 1 ? nq - 1 : 0; }   // the part of chunk j that piece j - 1 precedes
 template <class F>
 __device__ __forceinline__ void t2_schedule(const T2Geom& g, F&& f) {
   f(T2_OP_L1_STAGE, 0, 0);
@@ -182,17 +195,14 @@ __device__ __forceinline__ void t2_schedule(const T2Geom& g, F&& f) {
   f(T2_OP_L2_DONE, 0, 0);
 #pragma unroll
   for (int j = 1; j < g.NJ; ++j) {
-    f(T2_OP_L3_STAGE, j - 1, 0);                             // weights of piece j - 1, most of a chunk before they are used
-    // chunk j reuses the slot of chunk j - 2 (its first part waits until the epilogue has read that piece's partial last-layer
-    // product); the last-layer product of piece j - 1 is issued before the LAST part of chunk j, when the epilogue of chunk
-    // j - 1 has normally long finished, so neither side waits for the other
+    if (j >= 2) f(T2_OP_L3, j - 2, 0);                       // frees slot j & 1 (and the piece's weight stage)
+    f(T2_OP_L3_STAGE, j - 1, 0);                             // weights of piece j - 1, a whole chunk before they are used
+    const int parts = (g.cw(j) == 128) ? g.NQ : (g.NQ + 1) / 2;
 #pragma unroll
-    for (int p = 0; p < g.NQ; ++p) {
-      if (p == t2_l3_pos(g.NQ)) f(T2_OP_L3, j - 1, 0);
-      f(T2_OP_L2, j, p);
-    }
+    for (int p = 0; p < parts; ++p) f(T2_OP_L2, j, p);
     f(T2_OP_L2_DONE, j, 0);
   }
+  if (g.NJ >= 2) f(T2_OP_L3, g.NJ - 2, 0);
   f(T2_OP_L3_STAGE, g.NJ - 1, 0);
   f(T2_OP_L3, g.NJ - 1, 0);
 }
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
   // PTX predicate registers that carry the result of an early mbarrier.test_wait across the MMA block issued in between
   // (warps issue in order: converting the predicate to a value right away would stall the issuer for the ~100-cycle
   // latency of the test; see acquire() below)
-  asm volatile(".reg .pred t2_p_full;\n\t.reg .pred t2_p_sr;\n\t.reg .pred t2_p_w3;" ::);
+  asm volatile(".reg .pred t2_p_full;\n\t.reg .pred t2_p_sr;" ::);
   const ModelDims& md = a.md;
   const int D = md.D, Dv = md.Dv;
   float* zs = reinterpret_cast<float*>(smem + plan.off_zs);
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     ptx::mbar_init(&misc->a0r, 16);
     for (int i = 0; i < 4; ++i) { ptx::mbar_init(&misc->a1r[i], 16); ptx::mbar_init(&misc->l1f[i], 1); }
     for (int i = 0; i < 3; ++i) { ptx::mbar_init(&misc->sr[i], 16); ptx::mbar_init(&misc->l2f[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&misc->l3p[i], 1); ptx::mbar_init(&misc->sfree[i], 16); }
+    ptx::mbar_init(&misc->l3f, 1);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&misc->w3full[i], 1); ptx::mbar_init(&misc->w3empty[i], 1); }
     ptx::fence_mbar_init();
     if (a.G_ll != nullptr) mixture_coefficients(a.rho, a.n_mix, a.skip_c, a.mix_mode, misc->coef);
@@ -354,8 +364,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     const uint64_t a0_desc = ptx::make_smem_desc(ptx::smem_u32(A0));
     const uint64_t ring_desc = ptx::make_smem_desc(ptx::smem_u32(ring));
     const uint64_t w3_desc = ptx::make_smem_desc(ptx::smem_u32(w3buf));
-    uint32_t ph_w3f = 0, ph_sf = 0;
+    uint32_t ph_w3f = 0;
     const uint32_t idesc_l1 = ptx::make_idesc_f16(128, kT2Chunk);
+    const uint32_t idesc_l2 = ptx::make_idesc_f16(128, kT2Piece);
     int slot = 0;
     // An mbarrier test costs 100-160 cycles on this warp even when the phase has long completed, and tcgen05.mma issue is
     // nearly synchronous with execution (tools/tc_probe3.cu, tc_probe4.cu): every handshake between two MMA blocks idles
@@ -425,71 +436,79 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 m_iss += T2_CLOCK() - ti;
                 T2_TRACE(1 + x);
               } else if (op == T2_OP_L2) {
-                // layer-2 chunk x (slot x & 1), part y: A1 k-quarter y from TMEM x 8 k-slabs of [128 x 16]
-                // the A1 quarter of this part, and a slot free of layer-1 accumulators (slot 0 hosted the even chunks)
-                need_a1(max(y, x == 0 ? (G.l1_in_slot0 ? ((NQ - 1) & ~1) : 0) : NQ - 1));
-                if (x >= 2 && y == 0) {                                  // the slot still holds piece x - 2 and its partial product
-                  wait_epi(&misc->sfree[x & 1], (ph_sf >> (x & 1)) & 1u, 25);
-                  ph_sf ^= 1u << (x & 1);
-                }
-                if (x == NJ - 1) T2_TRACE(140 + 3 * y);
+                // layer-2 chunk x (slot x & 1), part y: A1 k-quarters from TMEM x k-slabs of [width x 16]
+                const int w = G.cw(x);
+                const int q0 = (w == 128) ? y : 2 * y;
+                const int nq = (w == 128) ? 1 : min(2, NQ - q0);
+                // the A1 quarters of this part, and a slot free of layer-1 accumulators (slot 0 hosted the even chunks)
+                need_a1(max(q0 + nq - 1, x == 0 ? (G.l1_in_slot0 ? ((NQ - 1) & ~1) : 0) : NQ - 1));
+                if (x == 3) T2_TRACE(130 + 3 * (y & 1));
                 const uint64_t bd = stage_take();
                 const int cur_slot = slot;
-                if (x == NJ - 1) T2_TRACE(141 + 3 * y);
-                // The op after part t2_l3_pos - 1 of chunk x >= 1 is the last-layer piece x - 1: test its two barriers (packed
-                // piece, weights) now, so that the latency of the tests overlaps with the MMAs issued below.
-                if (x >= 1 && y + 1 == t2_l3_pos(NQ)) {
+                if (x == 3) T2_TRACE(131 + 3 * (y & 1));
+                // The op after the LAST part of chunk x >= 1 is the last-layer piece x - 1: test its barrier
+                // now, so that its latency overlaps with the MMAs issued below instead of idling the pipe.
+                const bool pre_l3 = (q0 + nq == NQ) && x >= 1;
+                if (pre_l3) {
                   const int sn = (x - 1) & 1;
                   asm volatile("mbarrier.test_wait.parity.shared::cta.b64 t2_p_sr, [%0], %1;" ::"r"(ptx::smem_u32(&misc->sr[sn])),
                                "r"((ph_sr >> sn) & 1u) : "memory");
-                  asm volatile("mbarrier.test_wait.parity.shared::cta.b64 t2_p_w3, [%0], %1;" ::"r"(ptx::smem_u32(&misc->w3full[sn])),
-                               "r"((ph_w3f >> sn) & 1u) : "memory");
                   sr_pre = 1;
                 }
                 ti = T2_CLOCK();
                 if (ptx::elect_one()) {
                   const uint32_t d = tbase + G.slot_col[x & 1];
-                  const uint32_t at = tbase + (uint32_t)y * 64u;
-                  ptx::umma_f16_ts(d, at, bd, idesc_l1, y > 0 ? 1u : 0u);
+                  if (w == 128) {
+                    const uint32_t at = tbase + (uint32_t)q0 * 64u;
+                    ptx::umma_f16_ts(d, at, bd, idesc_l1, q0 > 0 ? 1u : 0u);
 #pragma unroll
-                  for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bd + (uint64_t)(i * 256), idesc_l1, 1u);
+                    for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bd + (uint64_t)(i * 256), idesc_l1, 1u);
+                  } else {
+                    for (int qq = 0; qq < nq; ++qq) {
+                      const uint32_t at = tbase + (uint32_t)(q0 + qq) * 64u;
+                      const uint64_t bq = bd + (uint64_t)(qq * 1024);
+                      ptx::umma_f16_ts(d, at, bq, idesc_l2, (q0 + qq) > 0 ? 1u : 0u);
+#pragma unroll
+                      for (int i = 1; i < 8; ++i) ptx::umma_f16_ts(d, at + 8u * i, bq + (uint64_t)(i * 128), idesc_l2, 1u);
+                    }
+                  }
                   ptx::umma_commit(&misc->empty[cur_slot]);
-                  if (y == NQ - 1) ptx::umma_commit(&misc->l2f[x & 1]);        // chunk complete -> epilogue
+                  if (q0 + nq == NQ) ptx::umma_commit(&misc->l2f[x & 1]);      // chunk complete -> epilogue
                 }
                 __syncwarp();
                 m_iss += T2_CLOCK() - ti;
-                if (x == NJ - 1) T2_TRACE(142 + 3 * y);
+                if (x == 3) T2_TRACE(132 + 3 * (y & 1));
               } else if (op == T2_OP_L2_DONE) {
                 T2_TRACE(10 + x);
               } else if (op == T2_OP_L3_STAGE) {
                 // producer-only op: the piece's weights go to their own buffer
               } else {
-                // last layer, k-piece x held packed in slot x & 1 (8 k-slabs at slot + 8 i): its product with W3's k-rows goes,
-                // NOT accumulated, to the upper half of the same slot
+                // last layer, k-piece x held packed in slot x & 1 (128-column chunk: 8 slabs at slot + 8 i; 64-column
+                // chunk: 4 slabs at slot + 16 i) -> last-layer accumulator
                 const int sl = x & 1;
+                const int w = G.cw(x);
                 if (x == 1) T2_TRACE(136);
                 ti = T2_CLOCK();
-                uint32_t sr_ok = 0, w3_ok = 0;
-                if (sr_pre) {
-                  asm volatile("selp.u32 %0, 1, 0, t2_p_sr;" : "=r"(sr_ok));
-                  asm volatile("selp.u32 %0, 1, 0, t2_p_w3;" : "=r"(w3_ok));
-                }
+                uint32_t sr_ok = 0;
+                if (sr_pre) asm volatile("selp.u32 %0, 1, 0, t2_p_sr;" : "=r"(sr_ok));
                 sr_pre = 0;
                 if (!sr_ok) ptx::mbar_wait(&misc->sr[sl], (ph_sr >> sl) & 1u, a.error_flag, 23);
+                ptx::tc_fence_after();
                 m_sr += T2_CLOCK() - ti;
                 ph_sr ^= 1u << sl;
                 if (x == 1) T2_TRACE(137);
-                if (!w3_ok) ptx::mbar_wait(&misc->w3full[sl], (ph_w3f >> sl) & 1u, a.error_flag, 24);   // landed a chunk ago
+                ptx::mbar_wait(&misc->w3full[sl], (ph_w3f >> sl) & 1u, a.error_flag, 24);   // landed a chunk ago
                 ptx::tc_fence_after();
                 ph_w3f ^= 1u << sl;
                 const uint64_t bd = w3_desc + (uint64_t)((uint32_t)sl * (kT2W3Bytes >> 4));
                 if (ptx::elect_one()) {
-                  const uint32_t at = tbase + G.slot_col[sl], d = at + 64u;
-#pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    ptx::umma_f16_ts(d, at + 8u * i, bd + (uint64_t)((uint32_t)i * b3_step), idesc_o, i > 0 ? 1u : 0u);
+                  const uint32_t at = tbase + G.slot_col[sl], d = tbase + G.la_col;
+                  const uint32_t astep = (w == 128) ? 8u : 16u;
+                  const int nsl = w >> 4;
+                  for (int i = 0; i < nsl; ++i)
+                    ptx::umma_f16_ts(d, at + astep * i, bd + (uint64_t)((uint32_t)i * b3_step), idesc_o, (x > 0 || i > 0) ? 1u : 0u);
                   ptx::umma_commit(&misc->w3empty[sl]);
-                  ptx::umma_commit(&misc->l3p[sl]);
+                  if (x == NJ - 1) ptx::umma_commit(&misc->l3f);
                 }
                 __syncwarp();
                 T2_TRACE(20 + x);
@@ -516,7 +535,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     const int dq = (D + 3) >> 2;
     const int h0col = min(D, g * dq), h1col = min(D, (g + 1) * dq);   // column split for elementwise passes
     uint32_t units = 0, stepc = 0;
-    uint32_t ph_l2f = 0, ph_l3p = 0;
+    uint32_t ph_l2f = 0;
     float* const part = reinterpret_cast<float*>(A0);   // per-row partial sums of a component's log-density (A0 is dead by then)
     float* const part2 = part + 3 * kTcRows;
     const uint32_t bstride = t2_bias_stride(md.h);
@@ -668,12 +687,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               }
             }
             // ---- layer 2: chunk j in slot j & 1 -> act -> fp16 pairs packed in place = k-piece j of the last layer's A
-            //      operand: 32 columns per thread compacted into slot[0:64) (the quadrant's four warps synchronise between
-            //      reading and overwriting) ----
-            float l3acc[16];                           // this thread's 16 last-layer columns, summed over the k-pieces
-#pragma unroll
-            for (int i = 0; i < 16; ++i) l3acc[i] = 0.f;
-            const int c0 = g * 16;
+            //      operand.  128-column chunk: 32 columns per thread compacted into slot[0:64) (the quadrant's four warps
+            //      synchronise between reading and overwriting); 64-column chunk: 16 columns per thread packed into the first
+            //      8 of the thread's own columns (no hazard) ----
             for (int j = 0; j < NJ; ++j) {
               const int sl = j & 1;
               e_tmp = T2_CLOCK();
@@ -685,7 +701,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               e_tmp = T2_CLOCK();
               const uint32_t sc = lane_base + G.slot_col[sl];
               const float* bj = bias_c + md.h + G.ccol(j);
-              {
+              if (G.cw(j) == 128) {
                 uint32_t p[16];
                 {
                   uint32_t r[32];
@@ -696,39 +712,36 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 }
                 t2_quad_bar(quad);             // all four threads of the row have read their columns
                 ptx::tmem_st16(sc + (uint32_t)g * 16u, p);
+              } else {
+                uint32_t p[8];
+                {
+                  uint32_t r[16];
+                  ptx::tmem_ld16(sc + (uint32_t)g * 16u, r);
+                  ptx::tmem_ld_wait();
+                  if (act_kind == 1) t2_act_pack16<1, TANH_MODE>(r, bj + g * 16, p);
+                  else               t2_act_pack16<2, TANH_MODE>(r, bj + g * 16, p);
+                }
+                ptx::tmem_st8(sc + (uint32_t)g * 16u, p);
               }
               ptx::tmem_st_wait();
               ptx::tc_fence_before();
               t2_warp_arrive(&misc->sr[sl], lane);
               if (tr) T2_TRACE(60 + 40 * (g & 1) + j);
               e_l2 += T2_CLOCK() - e_tmp;
-              // the last-layer product of this piece (issued by the MMA warp before the last part of the next chunk, or in the
-              // tail): add it to the register accumulators, then the slot may be overwritten by chunk j + 2
-              e_tmp = T2_CLOCK();
-              t2_wait(&misc->l3p[sl], (ph_l3p >> sl) & 1u, a.error_flag, 32, lane);
-              ph_l3p ^= 1u << sl;
-              if (tr && j == NJ - 1) T2_TRACE(70 + 40 * (g & 1));
-              e_w3 += T2_CLOCK() - e_tmp;
-              ptx::tc_fence_after();
-              if (c0 < np3) {
-                uint32_t r[16];
-                ptx::tmem_ld16(sc + 64u + (uint32_t)c0, r);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) l3acc[i] += __uint_as_float(r[i]);
-              }
-              if (j + 2 < NJ) {
-                ptx::tc_fence_before();
-                t2_warp_arrive(&misc->sfree[sl], lane);
-              }
             }
-            // ---- last layer: coupling transform on this thread's 16 columns; branch-free over the padded gather-order tables
-            //      (padded entries hit the scratch column and are masked out of the log-det) ----
+            // ---- last layer: coupling transform on this thread's 16-column slice of H(3); branch-free over the padded
+            //      gather-order tables (padded entries hit the scratch column and are masked out of the log-det) ----
             e_tmp = T2_CLOCK();
+            t2_wait(&misc->l3f, upar, a.error_flag, 32, lane);
+            if (tr) T2_TRACE(70 + 40 * (g & 1));
+            e_w3 += T2_CLOCK() - e_tmp;
+            ptx::tc_fence_after();
+            e_tmp = T2_CLOCK();
+            const int c0 = g * 16;
             if (c0 < np3) {
               uint32_t r[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(l3acc[i]);
+              ptx::tmem_ld16(lane_base + G.la_col + (uint32_t)c0, r);
+              ptx::tmem_ld_wait();
               // every branch: gather the affected z2 columns first, store them last (see the gather above)
               if (md.kind == GBNF_KIND_GLOW && md.coupling == GBNF_COUPLING_AFFINE) {
                 const float2* bias2 = reinterpret_cast<const float2*>(bias);

@@ -152,7 +152,7 @@ int plan_layout(gbnf_ctx* h) {
       for (StepDesc& sd : h->steps_h)
         for (int net = 0; net < md.nnets; ++net) {
           sd.layer[net][0].NC = kT2Chunk;
-          sd.layer[net][1].NC = kT2Chunk;
+          sd.layer[net][1].NC = kT2Chunk; sd.layer[net][1].NC2 = (md.h == 512) ? kT2Piece : 0;
         }
     } else if (!tc_make_plan(md, h->steps_h, &h->tc, &why)) {
       return fail(GBNF_ERR_INVALID, "f16 tensor-core path: " + why);

@@ -49,9 +49,6 @@ for i, n in enumerate(["L1 chunk 1: tcgen05.ld done", "L1 chunk 1: bias+act+pack
 for i, n in enumerate(["L2(4,h0) op start", "L2(4,h0) stage acquired", "L2(4,h0) 16 MMA issued", "L2(4,h1) op start", "L2(4,h1) stage acquired", "L2(4,h1) 16 MMA issued", "L3(1) op start", "L3(1) piece barrier passed"]):
     names[130 + i] = "MMA* " + n
 names[138] = "MMA* layer-1 weight stage taken"
-for y in range(4):
-    for i, n in enumerate(["op start", "stage acquired", "8 MMA issued"]):
-        names[140 + 3 * y + i] = f"MMA* L2(last chunk, part {y}) " + n
 ev = sorted((v, names[i]) for i, v in enumerate(t) if v > 0 and i in names)
 t0 = ev[0][0]
 print(f"{cfg_name} {mode}: one coupling pass of CTA 0 (cycles relative to first event)")
