@@ -16,7 +16,7 @@ COUPLING = {"affine": 0, "additive": 1}
 BASE_STD_NORMAL, BASE_DIAG_NORMAL = 0, 1
 GEMM = {"fp32": 0, "f16": 1, "f16fast": 2}
 WEIGHTS = {"density": 0, "toy": 1}
-MIX_SIMPLEX, MIX_RAW_RHO = 0, 1
+MIX_SIMPLEX, MIX_RAW_RHO, MIX_GEOMETRIC = 0, 1, 2
 
 
 class GbnfError(RuntimeError):
@@ -64,6 +64,7 @@ SIGNATURES = {
     "gbnf_weight_renorm": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),
     "gbnf_resample": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "gbnf_gather_rows": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "gbnf_actnorm_init": (C.c_int, [_vp, _i64, _i32, C.c_float, _vp, _vp, _vp]),
     "gbnf_sample_component": (C.c_int, [C.POINTER(_f32), _i32, _f64, _i32, C.POINTER(_i32)]),
     "gbnf_get_info": (C.c_int, [_vp, C.POINTER(Info)]),
     "gbnf_get_profile": (C.c_int, [_vp, C.POINTER(C.c_int64)]),

@@ -268,12 +268,15 @@ class BoostedFlow(nn.Module):
         return out
 
     @torch.no_grad()
-    def mixture_from_logq(self, logq, n_comp, skip_c=-1, raw_rho=False):
+    def mixture_from_logq(self, logq, n_comp, skip_c=-1, raw_rho=False, geometric=False):
+        """Mixture log-density from materialised log q_c: the logsumexp recursion (default / raw_rho), or the rho-weighted
+        mean of log q_c that utils/density_plotting.py:199-226 plots for the whole model (geometric=True)."""
         logq = _f32c(logq)
         G = torch.empty(logq.shape[0], device=logq.device, dtype=torch.float32)
         rho = self.rho.detach().to(logq.device, torch.float32).contiguous()
         _lib.check(_lib.load().gbnf_mixture_logdensity(self.handle(logq.device), _ptr(logq), logq.shape[0], logq.shape[1],
                                                        n_comp, _ptr(rho), skip_c,
+                                                       _lib.MIX_GEOMETRIC if geometric else
                                                        _lib.MIX_RAW_RHO if raw_rho else _lib.MIX_SIMPLEX, _ptr(G),
                                                        _stream(logq.device)))
         return G

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "pack.cuh"
 #include "mixture.cuh"
+#include "actnorm_init.cuh"
 #include "coupling_fp32.cuh"
 #include "coupling_tc.cuh"
 #include "coupling_tc2.cuh"
@@ -430,6 +431,9 @@ int gbnf_mixture_logdensity(gbnf_handle h, const float* d_logq, int64_t B, int32
   if (!h) return fail(GBNF_ERR_INVALID, "null handle");
   if (B < 0 || n_comp < 0 || n_comp > kMaxComponents || ld < n_comp) return fail(GBNF_ERR_INVALID, "bad B / n_comp / ld");
   if (skip_c == 0) return fail(GBNF_ERR_INVALID, "skip_c == 0 is not reachable in the reference (toy_experiment.py:409)");
+  if (mix_mode < GBNF_MIX_SIMPLEX || mix_mode > GBNF_MIX_GEOMETRIC) return fail(GBNF_ERR_INVALID, "bad mix_mode");
+  if (mix_mode == GBNF_MIX_GEOMETRIC && (skip_c >= 0 || n_comp == 0))
+    return fail(GBNF_ERR_INVALID, "the geometric mixture (utils/density_plotting.py:199-226) takes >= 1 component and no skip_c");
   if (B == 0) return GBNF_OK;
   if (!d_G_ll || (n_comp > 0 && (!d_logq || !d_rho))) return fail(GBNF_ERR_INVALID, "null pointer");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -445,6 +449,9 @@ int gbnf_fused_eval(gbnf_handle h, const float* d_x, int64_t B, int32_t n_comp, 
   if (!h) return fail(GBNF_ERR_INVALID, "null handle");
   if (B < 0 || n_comp < 0 || n_comp > h->cfg.C) return fail(GBNF_ERR_INVALID, "bad B / n_comp");
   if (skip_c == 0) return fail(GBNF_ERR_INVALID, "skip_c == 0 is not reachable in the reference (toy_experiment.py:409)");
+  if (mix_mode != GBNF_MIX_SIMPLEX && mix_mode != GBNF_MIX_RAW_RHO)
+    return fail(GBNF_ERR_INVALID, "fused path: mix_mode must be GBNF_MIX_SIMPLEX or GBNF_MIX_RAW_RHO (the geometric mixture works "
+                                  "on materialised log q: gbnf_component_logq + gbnf_mixture_logdensity)");
   if (B == 0) return GBNF_OK;
   if (!d_G_ll) return fail(GBNF_ERR_INVALID, "null G_ll");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -534,6 +541,30 @@ int gbnf_gather_rows(gbnf_handle h, const float* d_x, int32_t D, const int64_t* 
       d_x, D, (const long long*)d_idx, n, d_out);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
+  return GBNF_OK;
+}
+
+int gbnf_actnorm_init(const float* d_x, int64_t B, int32_t D, float scale, float* d_bias, float* d_logs, void* stream) {
+  if (B <= 0 || D <= 0 || D > kAnThreads || !(scale > 0.f)) return fail(GBNF_ERR_INVALID, "actnorm init: need B >= 1, 1 <= D <= 256, scale > 0");
+  if (!d_x || !d_bias || !d_logs) return fail(GBNF_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int Dp = 1;
+  while (Dp < D) Dp <<= 1;
+  const int rpb = kAnThreads / Dp;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((B + rpb - 1) / rpb, (long long)sms * 8));
+  double* acc = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&acc, 2 * (size_t)D * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(acc, 0, 2 * (size_t)D * sizeof(double), st));
+  actnorm_colsum_kernel<false><<<grid, kAnThreads, 0, st>>>(d_x, B, D, Dp, nullptr, acc);
+  actnorm_bias_kernel<<<(D + 63) / 64, 64, 0, st>>>(acc, B, D, d_bias);
+  actnorm_colsum_kernel<true><<<grid, kAnThreads, 0, st>>>(d_x, B, D, Dp, d_bias, acc + D);
+  actnorm_logs_kernel<<<(D + 63) / 64, 64, 0, st>>>(acc + D, B, D, scale, d_logs);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(acc, st);
+  if (e != cudaSuccess) return fail(GBNF_ERR_CUDA, cudaGetErrorString(e));
   return GBNF_OK;
 }
 

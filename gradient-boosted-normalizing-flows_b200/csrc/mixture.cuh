@@ -49,10 +49,40 @@ __global__ void __launch_bounds__(kMixThreads) mixture_lse_kernel(const float* _
                                                                  int n, const float* __restrict__ rho, int skip_c,
                                                                  int mix_mode, float* __restrict__ G_ll) {
   __shared__ float coef[kMaxComponents];
-  if (threadIdx.x == 0) mixture_coefficients(rho, n, skip_c, mix_mode, coef);
+  __shared__ float rho_sum;
+  if (threadIdx.x == 0) {
+    if (mix_mode == GBNF_MIX_GEOMETRIC) {
+      // utils/density_plotting.py:199-226: total += log_prob_c * rho_c over the components with rho_c != 0, then / sum(rho[0:n])
+      float s = 0.f;
+      for (int c = 0; c < n; ++c) { coef[c] = rho[c]; s += rho[c]; }
+      rho_sum = s;
+    } else {
+      mixture_coefficients(rho, n, skip_c, mix_mode, coef);
+    }
+  }
   __syncthreads();
   const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logq) & 15) == 0);
   const long long stride = (long long)gridDim.x * blockDim.x;
+  if (mix_mode == GBNF_MIX_GEOMETRIC) {
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += stride) {
+      const float* row = logq + b * ld;
+      float acc = 0.f;
+      int c = 0;
+      if (vec) {
+        for (; c + 4 <= n; c += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
+          // separate multiply and add, in component order: the reference's `total_prob += log_prob * rho[c]`
+          if (coef[c] != 0.f) acc = __fadd_rn(acc, __fmul_rn(v.x, coef[c]));
+          if (coef[c + 1] != 0.f) acc = __fadd_rn(acc, __fmul_rn(v.y, coef[c + 1]));
+          if (coef[c + 2] != 0.f) acc = __fadd_rn(acc, __fmul_rn(v.z, coef[c + 2]));
+          if (coef[c + 3] != 0.f) acc = __fadd_rn(acc, __fmul_rn(v.w, coef[c + 3]));
+        }
+      }
+      for (; c < n; ++c) if (coef[c] != 0.f) acc = __fadd_rn(acc, __fmul_rn(__ldg(row + c), coef[c]));
+      G_ll[b] = acc / rho_sum;
+    }
+    return;
+  }
   if (vec && n <= 16) {
     // all terms of a row in registers: exact max, then one ex2 per term and one lg2 per row (MUFU); two rows in flight
     const int nv = (n + 3) >> 2;

@@ -50,7 +50,13 @@ enum {
   GBNF_GEMM_F16_TC_FAST = 2 /* same GEMMs, tanh.approx.f32 (one MUFU op, rel err 2^-11): <= 2e-4 rel on log q      */
 };
 enum { GBNF_WEIGHTS_DENSITY = 0, GBNF_WEIGHTS_TOY = 1 }; /* density_experiment.py:627-641 | toy_experiment.py:440-459 */
-enum { GBNF_MIX_SIMPLEX = 0, GBNF_MIX_RAW_RHO = 1 };     /* density_experiment.py:618 | models/boosted_flow.py:132-133 */
+enum {
+  GBNF_MIX_SIMPLEX = 0,   /* logsumexp_c(log(rho_c / sum rho) + log q_c): density_experiment.py:612-622              */
+  GBNF_MIX_RAW_RHO = 1,   /* the un-normalised-rho recursion of _rho_gradients: models/boosted_flow.py:132-133       */
+  GBNF_MIX_GEOMETRIC = 2  /* sum_c rho_c log q_c / sum_c rho_c (components with rho_c == 0 left out): the "all
+                             components" panel of plot_boosted_fwd_flow_density, utils/density_plotting.py:199-226;
+                             only on materialised log q (gbnf_mixture_logdensity), not in gbnf_fused_eval          */
+};
 
 typedef struct {
   int32_t kind;      /* GBNF_KIND_* */
@@ -118,7 +124,9 @@ int gbnf_component_logq(gbnf_handle h, const float* d_x, int64_t B, int32_t c0, 
  * the 2-term logsumexp recursion of density_experiment.py:612-622 / :561-571 evaluated in its flat form
  * G = logsumexp_c(coef_c + logq_c).  d_rho is the RAW rho buffer [>= n_comp] (device);
  * skip_c >= 0 leaves that component out as toy_experiment.py:414-417 does (-1: none);
- * mix_mode GBNF_MIX_RAW_RHO reproduces BoostedFlow._rho_gradients (models/boosted_flow.py:124-134).
+ * mix_mode GBNF_MIX_RAW_RHO reproduces BoostedFlow._rho_gradients (models/boosted_flow.py:124-134);
+ * GBNF_MIX_GEOMETRIC returns the rho-weighted MEAN of log q_c (the log of the grid density that
+ * utils/density_plotting.py:185-226 plots for the whole model).
  * n_comp == 0 writes zeros (density_experiment.py:612). */
 int gbnf_mixture_logdensity(gbnf_handle h, const float* d_logq, int64_t B, int32_t ld, int32_t n_comp,
                             const float* d_rho, int32_t skip_c, int32_t mix_mode, float* d_G_ll, void* stream);
@@ -155,6 +163,11 @@ int gbnf_resample(gbnf_handle h, const float* d_w, int64_t B, const double* d_u,
 /* x_resampled = x[idx] (density_experiment.py:644). d_out [n, D]. */
 int gbnf_gather_rows(gbnf_handle h, const float* d_x, int32_t D, const int64_t* d_idx, int64_t n, float* d_out,
                      void* stream);
+
+/* Data-dependent ActNorm initialisation from one batch (ActNorm.initialize_parameters, models/layers.py:473-486):
+ * bias[c] = -mean_B x[:, c]; logs[c] = log(scale / (sqrt(mean_B (x[:, c] + bias[c])^2) + 1e-6)).  d_x [B, D], d_bias / d_logs [D]
+ * (device).  Needs no handle: it runs on the CURRENT device, on the caller's stream, before any component is packed. */
+int gbnf_actnorm_init(const float* d_x, int64_t B, int32_t D, float scale, float* d_bias, float* d_logs, void* stream);
 
 /* Host helper: component id under the same CDF rule for "1:c" / "1:c-1" / "-c" (models/boosted_flow.py:76-91).
  * rho_host is a HOST array; exclude >= 0 zeroes that entry first. */

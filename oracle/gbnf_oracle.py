@@ -218,6 +218,20 @@ def mixture_flat(logq, rho, n, skip_c=-1, normalized=True):
     return m + np.log(np.sum(np.exp(t - m[:, None]), axis=1))
 
 
+def mixture_geometric(logq, rho, n):
+    """Log of the 'all components' grid density of plot_boosted_fwd_flow_density (utils/density_plotting.py:199-226):
+    total = sum_c logq[:, c] * rho[c] over the first n components with rho[c] != 0 (accumulated in component order, in the
+    dtype of logq), divided by sum(rho[0:n]).  The reference plots exp() of this."""
+    dt = logq.dtype
+    rho = np.asarray(rho, dtype=dt)
+    total = np.zeros(logq.shape[0], dtype=dt)
+    for c in range(n):
+        if rho[c] == 0.0:
+            continue
+        total = total + logq[:, c] * rho[c]
+    return total / np.sum(rho[:n])
+
+
 # --------------------------------------------------------------------------------------
 # A.6  boosting weights
 # --------------------------------------------------------------------------------------

@@ -220,6 +220,42 @@ def build_case(name):
             out[tag + "batch_size"] = np.array(args.batch_size)
             for k in ("nll", "G_nll", "g_nll"):
                 out[tag + k] = np.array(float(losses[k]))
+        # grid density of the boosted model, geometric mixture (utils/density_plotting.py:185-226), through the reference's
+        # own plotting function with recording axes (matplotlib is stubbed: only the numbers are kept)
+        from utils import density_plotting as ref_plot
+        ref_plot.plt.cm = types.SimpleNamespace(viridis=lambda *a, **k: None)
+
+        class _Ax:
+            def __init__(self):
+                self.grids = []
+
+            def pcolormesh(self, xx, yy, prob, cmap=None):
+                self.grids.append(prob.clone())
+
+            def set_facecolor(self, *a, **k):
+                pass
+
+            def set_title(self, *a, **k):
+                pass
+
+        class _Axs(dict):
+            def __missing__(self, key):
+                self[key] = _Ax()
+                return self[key]
+
+        n_pts = 12
+        args.num_components = C
+        model.component, model.all_trained = C - 1, False
+        grid = ref_plot.setup_grid(4, n_pts, args)
+        axs = _Axs()
+        with torch.no_grad():
+            total = ref_plot.plot_boosted_fwd_flow_density(model, axs, grid, n_pts, 50, args)
+        plt_width = max(2, int(np.ceil(np.sqrt(C))))
+        out["grid.n_pts"] = np.array(n_pts)
+        out["grid.zz"] = grid[2].numpy()
+        out["grid.total_prob"] = total.numpy()
+        for c in range(C):
+            out[f"grid.prob.c{c}"] = axs[(int(1 + np.floor(c / plt_width)), int(c % plt_width))].grids[0].numpy()
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), |logq32-logq64|max = "

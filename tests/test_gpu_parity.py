@@ -186,6 +186,80 @@ def test_toy_objective_vs_golden(golden, models, mode):
             close(float(losses["nll"]), float(g[tag + ".nll"]), mode, "realnvp", scale=3.0)
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_grid_density_vs_golden(golden, models, mode):
+    """The reference's grid-density caller (utils/density_plotting.py:185-226, run by the reference itself for the fixture):
+    per-component densities and the geometric mixture, through the C ABI."""
+    import argparse
+    from gbnf_b200 import density_plotting as DP
+    g = golden("toy_d2"); model, md = models("toy_d2", mode)
+    C, n_pts = md["C"], int(g["grid.n_pts"])
+    model.component, model.all_trained = C - 1, False
+    grid = DP.setup_grid(4, n_pts, "cuda")
+    np.testing.assert_array_equal(grid[2].cpu().numpy(), g["grid.zz"])
+    total, probs = DP.boosted_fwd_flow_density(model, grid, n_pts, 50, argparse.Namespace(num_components=C))
+    tol = dict(rtol=2e-5, atol=1e-8) if mode == "fp32" else dict(rtol=3e-2, atol=1e-6)   # exp() of log q: F16_ATOL on log q
+    for c in range(C):
+        np.testing.assert_allclose(probs[c].numpy(), g[f"grid.prob.c{c}"], **tol)
+    np.testing.assert_allclose(total.numpy(), g["grid.total_prob"], **tol)
+    # the geometric mixture kernel alone, on the reference's own log q, incl. a component with rho == 0
+    logq = dev(np.log(np.stack([g[f"grid.prob.c{c}"].reshape(-1) for c in range(C)], 1)))
+    G = model.mixture_from_logq(logq, C, geometric=True)
+    np.testing.assert_allclose(G.cpu().numpy(), orc.mixture_geometric(logq.cpu().numpy(), md["rho"], C), rtol=1e-6, atol=1e-6)
+    rho0 = model.rho.clone()
+    try:
+        model.rho[2] = 0.0
+        G0 = model.mixture_from_logq(logq, C, geometric=True)
+        rho = md["rho"].copy(); rho[2] = 0.0
+        np.testing.assert_allclose(G0.cpu().numpy(), orc.mixture_geometric(logq.cpu().numpy(), rho, C), rtol=1e-6, atol=1e-6)
+    finally:
+        model.rho.copy_(rho0)
+    from gbnf_b200._lib import GbnfError
+    with pytest.raises(GbnfError):      # the fused path has no geometric mode
+        from gbnf_b200 import _lib
+        x = dev(g["grid.zz"]); out = torch.empty(x.shape[0], device="cuda")
+        _lib.check(_lib.load().gbnf_fused_eval(model.handle(x.device), x.data_ptr(), x.shape[0], C, model.rho.data_ptr(), -1,
+                                               _lib.MIX_GEOMETRIC, out.data_ptr(), None, None))
+
+
+@pytest.mark.parametrize("B,D", [(1, 3), (7, 1), (512, 43), (4096, 63), (100000, 6), (3000, 200)])
+def test_actnorm_init_vs_oracle(B, D):
+    """ActNorm.initialize_parameters (models/layers.py:473-486) as two fused column reductions."""
+    from gbnf_b200 import _lib
+    rng = np.random.default_rng(B + D)
+    x = (rng.standard_normal((B, D)) * rng.uniform(0.2, 5.0, D) + rng.uniform(-3, 3, D)).astype(np.float32)
+    xd = dev(x)
+    bias = torch.empty(D, device="cuda"); logs = torch.empty(D, device="cuda")
+    _lib.check(_lib.load().gbnf_actnorm_init(xd.data_ptr(), B, D, 1.5, bias.data_ptr(), logs.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream))
+    rb, rl = orc.actnorm_init(x.astype(np.float64), 1.5)
+    np.testing.assert_allclose(bias.cpu().numpy(), rb.reshape(-1), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(logs.cpu().numpy(), rl.reshape(-1), rtol=1e-5, atol=1e-5)
+    # through the host mirror's module (what the first training forward of a new component calls)
+    from gbnf_b200.flow_modules import ActNorm1d
+    m = ActNorm1d(D, scale=1.5).cuda().train()
+    y, ld = m(xd, torch.zeros(B, device="cuda"))
+    assert m.inited
+    np.testing.assert_allclose(m.bias.detach().cpu().numpy().reshape(-1), rb.reshape(-1), rtol=1e-5, atol=1e-6)
+    if B > 1:
+        np.testing.assert_allclose(y.detach().double().std(0, unbiased=False).cpu().numpy(), 1.5, rtol=1e-3)
+    with pytest.raises(_lib.GbnfError):
+        _lib.check(_lib.load().gbnf_actnorm_init(xd.data_ptr(), 0, D, 1.0, bias.data_ptr(), logs.data_ptr(), None))
+
+
+def test_actnorm_init_vs_reference_golden(golden):
+    """The reference initialised ActNorm of step 0 of every Glow component from x_init (make_golden.py: train-mode forwards,
+    density_experiment.py:346-356); the fixture holds the resulting parameters."""
+    from gbnf_b200 import _lib
+    g = golden("glow_d43")
+    x = dev(g["x_init"]); D = x.shape[1]
+    bias = torch.empty(D, device="cuda"); logs = torch.empty(D, device="cuda")
+    _lib.check(_lib.load().gbnf_actnorm_init(x.data_ptr(), x.shape[0], D, 1.0, bias.data_ptr(), logs.data_ptr(), None))
+    for c in range(3):
+        np.testing.assert_allclose(bias.cpu().numpy(), g[f"model.c{c}.k0.an_bias"].reshape(-1), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(logs.cpu().numpy(), g[f"model.c{c}.k0.an_logs"].reshape(-1), rtol=1e-5, atol=1e-6)
+
+
 # ---- BASELINE.json configurations against the oracle on seeded synthetic models -------------------------------------
 BASELINE_CONFIGS = {
     "cfg1_toy": dict(kind="realnvp", D=2, C=8, K=1, h=256, rho_init="uniform", toy_base=True),

@@ -95,6 +95,21 @@ def test_toy_objective(golden):
             assert abs(float(out[k]) - float(g[tag + "." + k])) < 2e-5 * max(1.0, abs(float(g[tag + "." + k])))
 
 
+def test_grid_density_geometric_mixture(golden):
+    """plot_boosted_fwd_flow_density (utils/density_plotting.py:185-226) run by the reference on a 12 x 12 grid."""
+    g = golden("toy_d2"); md = golden_model(g)
+    zz, C = g["grid.zz"], md["C"]
+    logq = orc.all_component_logq(md, zz)
+    for c in range(C):
+        np.testing.assert_allclose(np.exp(logq[:, c]).reshape(12, 12), g[f"grid.prob.c{c}"], rtol=2e-5, atol=1e-9)
+    total = np.exp(orc.mixture_geometric(logq, md["rho"], C)).reshape(12, 12)
+    np.testing.assert_allclose(total, g["grid.total_prob"], rtol=2e-5, atol=1e-9)
+    # a component with rho == 0 is left out of the sum but not of the normaliser (:200-201, :222)
+    rho = md["rho"].copy(); rho[2] = 0.0
+    ref = sum(logq[:, c] * rho[c] for c in range(C) if c != 2) / rho.sum()
+    np.testing.assert_allclose(orc.mixture_geometric(logq, rho, C), ref, rtol=1e-6)
+
+
 def test_properties():
     rng = np.random.default_rng(0)
     logq = rng.standard_normal((500, 6)).astype(np.float32) * 5 - 30
