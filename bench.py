@@ -8,7 +8,9 @@ fused per-component log q_c + rho-weighted logsumexp (one kernel) followed by th
 resident in HBM for `value` (the resident set, 2^20 rows, is larger than L2 and the batches rotate through it);
 `e2e` runs the same step through the public Python API from pinned HOST buffers with the H2D / D2H copies inside
 the timed region.  Multi-GPU = batch-parallel weak scaling: every rank evaluates its own batch, the boosting
-weights use the global softmax (three scalar all-reduces over NCCL).  One JSON line on stdout (rank 0).
+weights use the global softmax (three scalar all-reduces over NCCL); `--parallel component` shards the components
+instead (every rank sees the batch, one all-gather of [B, C/G] log q per step, strong scaling).  One JSON line on
+stdout (rank 0).
 """
 import argparse
 import json
@@ -217,7 +219,11 @@ def run_ours(a):
     # ---- model: random-init weights of the named architecture (product constructors, seed 1) -------------------
     torch.manual_seed(1)
     model = gbnf_b200.BoostedFlow(make_args(cfg, device), gemm_mode=a.mode).to(device)
-    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    comp_par = (a.parallel == "component" and world > 1)
+    if comp_par and C % world != 0:
+        raise SystemExit(f"--parallel component needs C % world == 0 (C = {C}, world = {world})")
+    # batch-parallel: every rank owns different rows; component-parallel: every rank sees the SAME rows
+    gen = torch.Generator(device=device).manual_seed(1234 + (0 if comp_par else rank))
     x_all = torch.randn((a.rows, D), device=device, generator=gen)
     model.train()
     with torch.no_grad():   # ActNorm data-dependent init from the first 4096 rows (density_experiment.py:346-356)
@@ -234,11 +240,14 @@ def run_ours(a):
 
     def step(xb, ev=None):
         if ev: ev[0].record()
-        G = model.mixture_log_density(xb, C)
-        if ev: ev[1].record()
-        if world > 1:
-            w = gd.boosting_weights_batch_parallel(ops, G, "density")
+        if comp_par:    # rank g: log q of components [g C/G, (g+1) C/G) -> all-gather [B, C/G] -> local mixture kernel
+            G = gd.mixture_component_parallel(ops, xb, C)
         else:
+            G = model.mixture_log_density(xb, C)
+        if ev: ev[1].record()
+        if world > 1 and not comp_par:
+            w = gd.boosting_weights_batch_parallel(ops, G, "density")
+        else:           # component-parallel: every rank holds the whole batch's G_ll, weights are computed redundantly
             w = model.boosting_weights(G)
         if ev: ev[2].record()
         return G, w
@@ -273,7 +282,8 @@ def run_ours(a):
     ms_total = ms_total.item()
     k_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / a.steps          # fused coupling+mixture kernel
     w_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / a.steps          # boosting-weight kernels
-    value = world * a.batch * a.steps / (ms_total * 1e-3)
+    job_rows = a.batch if comp_par else world * a.batch     # rows the whole job finishes per step
+    value = job_rows * a.steps / (ms_total * 1e-3)
 
     # ---- `e2e`: host buffers in, host result out, copies inside the timed region -------------------------------
     n_host = min(nb, 4)
@@ -316,7 +326,7 @@ def run_ours(a):
     e2e_ms = torch.tensor([max(s2.elapsed_time(e2), 0.0)], device=device)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * a.batch * a.steps / (e2e_ms.item() * 1e-3)
+    e2e_value = job_rows * a.steps / (e2e_ms.item() * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -324,7 +334,7 @@ def run_ours(a):
         return
     # ---- roofline of the dominant kernel --------------------------------------------------------------------
     pk = peaks()
-    fl = flops_per_sample(cfg) * a.batch
+    fl = flops_per_sample(cfg) * a.batch / (world if comp_par else 1)    # per GPU (component-parallel: C / world components)
     long_run = ms_total > 1000.0
     peak = pk["bf16_sustained"] if long_run else pk["bf16_burst"]
     achieved = fl / (k_ms * 1e-3) / 1e12
@@ -334,13 +344,16 @@ def run_ours(a):
         traffic = json.load(open(tpath)).get(f"{a.config}:{a.mode}:{a.batch}")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong" if comp_par else "weak",
+        "vs_baseline": None,
         "dtype": "f32" if a.mode == "fp32" else "f16 operands / f32 accumulate", "data": "synthetic",
         "config": {"workload": workload_name(a), "batch": a.batch, "rows_resident_per_gpu": a.rows, "gemm_mode": a.mode,
                    "l2": f"resident rows {a.rows * D * 4 / 1e6:.0f} MB per GPU > 126 MB L2; batches rotate through them",
-                   "parallelism": f"batch-parallel x{world} (weak: {a.batch} rows per GPU per step)"},
+                   "parallelism": (f"component-parallel x{world} ({C // world} of {C} components per GPU, every GPU sees all "
+                                   f"{a.batch} rows of a step; one NCCL all-gather of [B, C/G] log q per step)" if comp_par else
+                                   f"batch-parallel x{world} (weak: {a.batch} rows per GPU per step)")},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fused coupling+mixture", "kernel_ms": k_ms, "weights_ms": w_ms,
+                     "traffic": traffic, "kernel": "coupling (C/G components) + all-gather + mixture" if comp_par else "fused coupling+mixture", "kernel_ms": k_ms, "weights_ms": w_ms,
                      "flops_per_sample": flops_per_sample(cfg),
                      "peak_kind": ("sustained" if long_run else "burst") + " bf16, " + pk["source"]},
         "clocks": clocks,
@@ -366,6 +379,8 @@ def main():
     p.add_argument("--config", default="cfg3_miniboone", choices=list(CONFIGS))
     p.add_argument("--mode", default=os.environ.get("GBNF_BENCH_MODE", "f16fast"), choices=["f16", "f16fast", "fp32"])
     p.add_argument("--batch", type=int, default=65536)
+    p.add_argument("--parallel", default="batch", choices=["batch", "component"],
+                   help="N > 1: shard rows (default, weak scaling) or components (strong scaling, cfg4's layout)")
     p.add_argument("--rows", type=int, default=1 << 20)
     p.add_argument("--cpu-rows", type=int, default=524288)
     p.add_argument("--no-cpu", action="store_true")
