@@ -21,23 +21,25 @@ __device__ __forceinline__ float mixture_row_lse(const float4 (&v)[NV], int n, c
   for (int c = 0; c < 4 * NV; ++c) sum += __expf(t[c] - m);                // exp(-inf) = 0 for skipped / padded terms
   return (m == -INFINITY) ? 0.f : m + __logf(sum);
 }
-template <int NV>
+// R rows in flight per thread (all their 128-bit loads are issued before the first logsumexp): the kernel is a pure stream,
+// what it needs is bytes in flight
+template <int NV, int R>
 __device__ __forceinline__ void mixture_rows_small(const float* __restrict__ logq, long long B, int ld, int n, const float* coef,
                                                    float* __restrict__ G_ll, long long stride) {
   long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  for (; b + stride < B; b += 2 * stride) {
-    float4 v0[NV], v1[NV];
+  for (; b + (R - 1) * stride < B; b += R * stride) {
+    float4 v[R][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v0[i] = __ldg(reinterpret_cast<const float4*>(logq + b * ld) + i);
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v1[i] = __ldg(reinterpret_cast<const float4*>(logq + (b + stride) * ld) + i);
-    G_ll[b] = mixture_row_lse<NV>(v0, n, coef);
-    G_ll[b + stride] = mixture_row_lse<NV>(v1, n, coef);
+      for (int i = 0; i < NV; ++i) v[r][i] = __ldcs(reinterpret_cast<const float4*>(logq + (b + r * stride) * ld) + i);
+#pragma unroll
+    for (int r = 0; r < R; ++r) G_ll[b + r * stride] = mixture_row_lse<NV>(v[r], n, coef);
   }
-  if (b < B) {
+  for (; b < B; b += stride) {
     float4 v0[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v0[i] = __ldg(reinterpret_cast<const float4*>(logq + b * ld) + i);
+    for (int i = 0; i < NV; ++i) v0[i] = __ldcs(reinterpret_cast<const float4*>(logq + b * ld) + i);
     G_ll[b] = mixture_row_lse<NV>(v0, n, coef);
   }
 }
@@ -86,10 +88,10 @@ __global__ void __launch_bounds__(kMixThreads) mixture_lse_kernel(const float* _
   if (vec && n <= 16) {
     // all terms of a row in registers: exact max, then one ex2 per term and one lg2 per row (MUFU); two rows in flight
     const int nv = (n + 3) >> 2;
-    if (nv == 1) mixture_rows_small<1>(logq, B, ld, n, coef, G_ll, stride);
-    else if (nv == 2) mixture_rows_small<2>(logq, B, ld, n, coef, G_ll, stride);
-    else if (nv == 3) mixture_rows_small<3>(logq, B, ld, n, coef, G_ll, stride);
-    else mixture_rows_small<4>(logq, B, ld, n, coef, G_ll, stride);
+    if (nv == 1) mixture_rows_small<1, 4>(logq, B, ld, n, coef, G_ll, stride);
+    else if (nv == 2) mixture_rows_small<2, 4>(logq, B, ld, n, coef, G_ll, stride);
+    else if (nv == 3) mixture_rows_small<3, 2>(logq, B, ld, n, coef, G_ll, stride);
+    else mixture_rows_small<4, 2>(logq, B, ld, n, coef, G_ll, stride);
     return;
   }
   for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += stride) {
@@ -148,20 +150,30 @@ __global__ void __launch_bounds__(kMixThreads) softmax_stats_kernel(const float*
                                                                    float* __restrict__ ms_out /* [2] */) {
   __shared__ MsPair sm[32];
   __shared__ bool is_last;
-  // pass 1 (thread-local): two-sweep max / sum over a strided slice keeps exp() calls to one per element
+  // thread-local online (max, sum) over a strided slice, ONE sweep (G_ll is read from HBM once whatever its size): the
+  // running sum is rescaled only when a 128-bit group raises the maximum, so exp() stays at ~one call per element
   MsPair v; v.m = -INFINITY; v.s = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool vec = (reinterpret_cast<uintptr_t>(G_ll) & 15) == 0;
   const long long B4 = vec ? (B >> 2) : 0;                                 // 128-bit body, scalar tail
   const float4* G4 = reinterpret_cast<const float4*>(G_ll);
-  for (long long i = i0; i < B4; i += stride) { const float4 g = __ldg(G4 + i); v.m = fmaxf(v.m, -fminf(fminf(g.x, g.y), fminf(g.z, g.w))); }
-  for (long long i = 4 * B4 + i0; i < B; i += stride) v.m = fmaxf(v.m, -__ldg(G_ll + i));
-  for (long long i = i0; i < B4; i += stride) {
-    const float4 g = __ldg(G4 + i);                                        // second sweep: L2 hits for batch-sized inputs
-    v.s += (expf(-g.x - v.m) + expf(-g.y - v.m)) + (expf(-g.z - v.m) + expf(-g.w - v.m));
+  auto add4 = [&](const float4 g) {
+    const float gm = -fminf(fminf(g.x, g.y), fminf(g.z, g.w));
+    if (gm > v.m) { v.s = (v.m == -INFINITY) ? 0.f : v.s * expf(v.m - gm); v.m = gm; }
+    if (v.m != -INFINITY) v.s += (expf(-g.x - v.m) + expf(-g.y - v.m)) + (expf(-g.z - v.m) + expf(-g.w - v.m));
+  };
+  long long i = i0;
+  for (; i + 3 * stride < B4; i += 4 * stride) {                          // four 128-bit loads in flight per thread
+    const float4 g0 = __ldg(G4 + i), g1 = __ldg(G4 + i + stride), g2 = __ldg(G4 + i + 2 * stride), g3 = __ldg(G4 + i + 3 * stride);
+    add4(g0); add4(g1); add4(g2); add4(g3);
   }
-  for (long long i = 4 * B4 + i0; i < B; i += stride) v.s += expf(-__ldg(G_ll + i) - v.m);
+  for (; i < B4; i += stride) add4(__ldg(G4 + i));
+  for (long long j = 4 * B4 + i0; j < B; j += stride) {
+    const float u = -__ldg(G_ll + j);
+    if (u > v.m) { v.s = (v.m == -INFINITY) ? 0.f : v.s * expf(v.m - u); v.m = u; }
+    if (v.m != -INFINITY) v.s += expf(u - v.m);
+  }
   MsPair r = ms_block_reduce(v, sm);
   if (threadIdx.x == 0) {
     partial[2 * blockIdx.x] = r.m;
@@ -200,8 +212,8 @@ __global__ void __launch_bounds__(kMixThreads) weight_apply_kernel(const float* 
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool vec = ((reinterpret_cast<uintptr_t>(G_ll) | reinterpret_cast<uintptr_t>(w)) & 15) == 0;
   const long long B4 = vec ? (B >> 2) : 0;                                 // 128-bit body, scalar tail
-  for (long long i = i0; i < B4; i += stride) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(G_ll) + i);
+  const float4* G4 = reinterpret_cast<const float4*>(G_ll);
+  auto apply4 = [&](const float4 g, long long i) {
     float4 v;
     v.x = expf(-g.x - M) / S; v.y = expf(-g.y - M) / S; v.z = expf(-g.z - M) / S; v.w = expf(-g.w - M) / S;
     if (clamp) {
@@ -210,7 +222,13 @@ __global__ void __launch_bounds__(kMixThreads) weight_apply_kernel(const float* 
     }
     reinterpret_cast<float4*>(w)[i] = v;
     acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+  };
+  long long i = i0;
+  for (; i + 3 * stride < B4; i += 4 * stride) {                          // four 128-bit loads in flight per thread
+    const float4 g0 = __ldg(G4 + i), g1 = __ldg(G4 + i + stride), g2 = __ldg(G4 + i + 2 * stride), g3 = __ldg(G4 + i + 3 * stride);
+    apply4(g0, i); apply4(g1, i + stride); apply4(g2, i + 2 * stride); apply4(g3, i + 3 * stride);
   }
+  for (; i < B4; i += stride) apply4(__ldg(G4 + i), i);
   for (long long i = 4 * B4 + i0; i < B; i += stride) {
     float v = expf(-__ldg(G_ll + i) - M) / S;
     if (clamp) v = fmaxf(fminf(v, hi), lo);
@@ -240,11 +258,14 @@ __global__ void __launch_bounds__(kMixThreads) weight_renorm_kernel(float* __res
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long B4 = ((reinterpret_cast<uintptr_t>(w) & 15) == 0) ? (B >> 2) : 0;
-  for (long long i = i0; i < B4; i += stride) {
-    float4 v = reinterpret_cast<float4*>(w)[i];
-    v.x = v.x / s; v.y = v.y / s; v.z = v.z / s; v.w = v.w / s;
-    reinterpret_cast<float4*>(w)[i] = v;
+  float4* w4 = reinterpret_cast<float4*>(w);
+  auto div4 = [&](float4 v, long long i) { v.x = v.x / s; v.y = v.y / s; v.z = v.z / s; v.w = v.w / s; w4[i] = v; };
+  long long i = i0;
+  for (; i + 3 * stride < B4; i += 4 * stride) {                          // four 128-bit loads in flight per thread
+    const float4 v0 = w4[i], v1 = w4[i + stride], v2 = w4[i + 2 * stride], v3 = w4[i + 3 * stride];
+    div4(v0, i); div4(v1, i + stride); div4(v2, i + 2 * stride); div4(v3, i + 3 * stride);
   }
+  for (; i < B4; i += stride) div4(w4[i], i);
   for (long long i = 4 * B4 + i0; i < B; i += stride) w[i] = w[i] / s;
 }
 
