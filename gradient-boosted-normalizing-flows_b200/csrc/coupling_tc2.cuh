@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             }
             t2_epi_bar();
           }
-          for (int i = et; i < total; i += kT2EpiThreads) { const int r = i / D; zs[r * Dv + (i - r * D)] = xs[i]; }
+          for (int p = h0col; p < h1col; ++p) zrow[p] = xs[row * D + p];   // this thread's quarter of its own row (no div / mod)
           if (g == 0) for (int p = D; p < Dv; ++p) zrow[p] = 0.f;         // scratch column(s): target of padded table entries
         }
         ptx::cp_async_wait_all();                    // (first component of the launch: the prologue's staging copies)
