@@ -48,6 +48,8 @@ struct CompDesc {
   long long sigma_off;   // iblob: final logical->physical map [D]
   long long const_off;   // fblob: [0] = sum of all data-independent log-det terms, [1] = packed flag
   long long base_off;    // fblob: mean_phys[Dv] | inv2var_phys[Dv]  (toy base), [2*Dv] = -sum(log s) - D/2 log 2pi
+  long long dense_off;   // fblob: {fblob[const_off], fblob[base_off + 2*Dv]} again, in a dense per-component float2 table
+                         // (CouplingArgs::cc_off + 2 c): one independent load instead of descriptor -> offset -> value
 };
 
 struct ModelDims {
@@ -67,6 +69,7 @@ struct CouplingArgs {
   const float* fblob;
   const int* iblob;
   const void* wblob;
+  long long cc_off;                // fblob: dense float2 table of per-component constants (CompDesc::dense_off)
   ModelDims md;
   int num_tiles;
   // pipelined kernel only: a row tile's components are split over `split` work units (better wave quantisation, more

@@ -560,6 +560,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
         // ---- x tile: fetched from HBM once per tile (8 independent loads in flight per thread) and kept in shared
         //      memory; every component restarts from it ----
         e_tmp = T2_CLOCK();
+        // the component's scalars for the END of the component, fetched now with independent loads: three dependent L2 round
+        // trips there (descriptor -> offsets -> constants) would sit on the critical path of every component
+        const CompDesc* cdp = a.comps + c;
+        const float2 cconst = __ldg(reinterpret_cast<const float2*>(a.fblob + a.cc_off) + c);   // {ldj constant, base constant}
+        const long long base_off = (md.base == GBNF_BASE_STD_NORMAL) ? 0LL : __ldg(&cdp->base_off);
+        const float ldj_const = cconst.x, base_const = cconst.y;
         t2_epi_bar();                                // previous component's readers are done with zs / part
         {
           const int total = kTcRows * D;
@@ -805,18 +811,20 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           }
         }
         // ---- component log-density for this row ----
-        const CompDesc& cd = a.comps[c];
-        const float* bm = a.fblob + cd.base_off;
-        const float* bi = bm + Dv;
         float q = 0.f;
-        for (int p = h0col; p < h1col; ++p) { const float d = zrow[p] - __ldg(bm + p); q = fmaf(d * d, __ldg(bi + p), q); }
+        if (md.base == GBNF_BASE_STD_NORMAL) {       // mean 0, 1 / (2 var) = 0.5: the same arithmetic as the table path, no loads
+          for (int p = h0col; p < h1col; ++p) { const float d = zrow[p]; q = fmaf(d * d, 0.5f, q); }
+        } else {
+          const float* bm = a.fblob + base_off;
+          const float* bi = bm + Dv;
+          for (int p = h0col; p < h1col; ++p) { const float d = zrow[p] - __ldg(bm + p); q = fmaf(d * d, __ldg(bi + p), q); }
+        }
         if (g > 0) { part[(g - 1) * kTcRows + row] = q; part2[(g - 1) * kTcRows + row] = lsum; }
         t2_quad_bar(quad);
         if (g == 0) {
           q += part[row] + part[kTcRows + row] + part[2 * kTcRows + row];
-          const float ldj_tot = (lsum + part2[row] + part2[kTcRows + row] + part2[2 * kTcRows + row]) +
-                                __ldg(a.fblob + cd.const_off);
-          const float lq = (__ldg(bm + 2 * Dv) - q) + ldj_tot;
+          const float ldj_tot = (lsum + part2[row] + part2[kTcRows + row] + part2[2 * kTcRows + row]) + ldj_const;
+          const float lq = (base_const - q) + ldj_tot;
           if (gr < a.B) {
             if (a.logq) a.logq[gr * a.ld_logq + (c - a.c0)] = lq;
             if (a.ldj_out) a.ldj_out[gr] = ldj_tot;
@@ -824,7 +832,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           if (a.G_ll != nullptr && c < a.n_mix) __stcg(a.lse_terms + ((long long)tile * kTcRows + row) * a.n_mix + c, misc->coef[c] + lq);
         }
         if (a.z_out != nullptr && gr < a.B) {
-          const int* sig = a.iblob + cd.sigma_off;
+          const int* sig = a.iblob + __ldg(&cdp->sigma_off);
           for (int j = h0col; j < h1col; ++j) a.z_out[gr * D + j] = zrow[__ldg(sig + j)];
         }
       }

@@ -50,7 +50,7 @@ struct gbnf_ctx {
   float* fblob = nullptr;
   int* iblob = nullptr;
   void* wblob = nullptr;
-  long long f_count = 0, i_count = 0, w_bytes = 0;
+  long long f_count = 0, i_count = 0, w_bytes = 0, cc_off = 0;
   const float* base_mean = nullptr;
   const float* base_scale = nullptr;
   gbnf_step_params* step_params_d = nullptr;
@@ -132,6 +132,10 @@ int plan_layout(gbnf_ctx* h) {
     cd.const_off = f; f += 4;
     cd.base_off = f; f += round_up_ll(2LL * md.Dv + 1, 4);
   }
+  f = round_up_ll(f, 4);
+  h->cc_off = f;
+  for (int cc = 0; cc < c.C; ++cc) h->comps_h[cc].dense_off = f + 2LL * cc;
+  f += round_up_ll(2LL * c.C, 4);
   h->f_count = f; h->i_count = i;
   h->w_bytes = w * (f16 ? (long long)sizeof(__half) : (long long)sizeof(float));
   if (!f16) {
@@ -207,6 +211,7 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
   a.x = x; a.B = B; a.c0 = c0; a.c1 = c1; a.logq = logq; a.ld_logq = ld_logq; a.z_out = z_out; a.ldj_out = ldj_out;
   a.rho = rho; a.n_mix = n_mix; a.skip_c = skip_c; a.mix_mode = mix_mode; a.G_ll = G_ll;
   a.steps = h->steps_d; a.comps = h->comps_d; a.fblob = h->fblob; a.iblob = h->iblob; a.wblob = h->wblob; a.md = h->md;
+  a.cc_off = h->cc_off;
   a.error_flag = h->flags;
   { const char* ee = std::getenv("GBNF_EXP"); a.exp_flags = ee ? std::atoi(ee) : 0; }
   a.prof = h->prof;

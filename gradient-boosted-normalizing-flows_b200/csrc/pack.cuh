@@ -107,6 +107,8 @@ __global__ void pack_meta_kernel(PackMetaArgs a) {
     for (int j = 0; j < D; ++j) bi[sigma[j]] = 0.5f;
   }
   bm[2 * Dv] = (float)c0;
+  a.fblob[a.cdesc.dense_off] = (float)ldj_const;
+  a.fblob[a.cdesc.dense_off + 1] = (float)c0;
 }
 
 // fp32 path: dst[k][n] = W[n][k] (zero padded).
