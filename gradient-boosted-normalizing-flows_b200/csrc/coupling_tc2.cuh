@@ -885,6 +885,7 @@ inline cudaError_t tc2_configure() {
 #define T2_CFG(T, P, Q) if (e == cudaSuccess) e = tc2_configure_one<T, P, Q>()
   T2_CFG(0, 0, 0); T2_CFG(1, 0, 0); T2_CFG(0, 1, 0); T2_CFG(1, 1, 0); T2_CFG(0, 2, 0); T2_CFG(1, 2, 0);
   T2_CFG(0, 0, 4); T2_CFG(1, 0, 4); T2_CFG(0, 1, 4); T2_CFG(1, 1, 4); T2_CFG(0, 2, 4); T2_CFG(1, 2, 4);
+  T2_CFG(0, 0, 2); T2_CFG(1, 0, 2);
 #undef T2_CFG
   return e;
 }
@@ -892,8 +893,11 @@ inline cudaError_t tc2_configure() {
 inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStream_t st, int prof) {
 #define T2_GO(T, P, Q) coupling_tc2_kernel<T, P, Q><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p)
 #define T2_GO_Q(T, P) do { if (a.md.h == 512) T2_GO(T, P, 4); else T2_GO(T, P, 0); } while (0)
-  if (p.tanh_mode == 0) { if (prof == 1) T2_GO_Q(0, 1); else if (prof == 2) T2_GO_Q(0, 2); else T2_GO_Q(0, 0); }
-  else                  { if (prof == 1) T2_GO_Q(1, 1); else if (prof == 2) T2_GO_Q(1, 2); else T2_GO_Q(1, 0); }
+  // production builds of the two widths the BASELINE configurations use are specialised (h = 512: NQT = 4, h = 256: NQT = 2)
+#define T2_GO_PROD(T) do { if (a.md.h == 512) T2_GO(T, 0, 4); else if (a.md.h == 256) T2_GO(T, 0, 2); else T2_GO(T, 0, 0); } while (0)
+  if (p.tanh_mode == 0) { if (prof == 1) T2_GO_Q(0, 1); else if (prof == 2) T2_GO_Q(0, 2); else T2_GO_PROD(0); }
+  else                  { if (prof == 1) T2_GO_Q(1, 1); else if (prof == 2) T2_GO_Q(1, 2); else T2_GO_PROD(1); }
+#undef T2_GO_PROD
 #undef T2_GO_Q
 #undef T2_GO
   return 0;
