@@ -247,7 +247,9 @@ __device__ __forceinline__ void t2_stage_bias_async(float* dst, const float* src
 // NQT: h / 128 as a compile-time constant (0 = read it from the model): with a constant geometry the whole schedule unrolls
 // into straight-line code, which matters on the MMA-issuer warp where every dependent scalar instruction costs 4-6 cycles
 // that are NOT hidden whenever a stage is issue-bound (measured ~400 cycles of bookkeeping per stage in the generic form).
-template <int TANH_MODE, int PROF, int NQT>
+// GA: the model is known at compile time to be Glow / affine coupling / tanh nets (one net per step): the other coupling
+// variants, activations and the two-net RealNVP control flow drop out of the instantiation.
+template <int TANH_MODE, int PROF, int NQT, bool GA = false>
 __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArgs a, TcPlan plan) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // PTX predicate registers that carry the result of an early mbarrier.test_wait across the MMA block issued in between
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
   asm volatile(".reg .pred t2_p_full;\n\t.reg .pred t2_p_sr;" ::);
   const ModelDims& md = a.md;
   const int D = md.D, Dv = md.Dv;
+  const int nnets = GA ? 1 : md.nnets;
   float* zs = reinterpret_cast<float*>(smem + plan.off_zs);
   unsigned char* A0 = smem + plan.off_a0;
   float* xs = reinterpret_cast<float*>(smem + plan.off_a1);
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
       for (int c = cb; c < ce; ++c)
         for (int k = 0; k < md.K; ++k) {
           const StepDesc* sd = a.steps + (c * md.K + k);
-          for (int net = 0; net < md.nnets; ++net) {
+          for (int net = 0; net < nnets; ++net) {
             const int k0s = __ldg(&sd->layer[net][0].Kp) >> 4;
             const int np3 = __ldg(&sd->layer[net][2].Np);
             const __half* w1 = wb + __ldg(&sd->layer[net][0].w_off);
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
       for (int c = cb; c < ce; ++c)
         for (int k = 0; k < md.K; ++k) {
           const StepDesc* sd = a.steps + (c * md.K + k);
-          for (int net = 0; net < md.nnets; ++net, ++units) {
+          for (int net = 0; net < nnets; ++net, ++units) {
             const int k0s = __ldg(&sd->layer[net][0].Kp) >> 4;
             const int np3 = __ldg(&sd->layer[net][2].Np);
             const uint32_t idesc_o = ptx::make_idesc_f16(128, np3);
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
       const int cb0 = a.c0 + ((int)blockIdx.x % a.split) * a.comps_per_unit;
       const StepDesc* sd0 = a.steps + cb0 * md.K;
       if (et < 2 * kEpPad) ptx::cp_async16(tab_s + et, reinterpret_cast<const float4*>(a.fblob + __ldg(&sd0->ep_off)) + et);
-      if (et == 0) t2_stage_meta(sd0, md.nnets, misc->meta[0]);
+      if (et == 0) t2_stage_meta(sd0, nnets, misc->meta[0]);
       t2_stage_bias_async(bias_s, a.fblob + __ldg(&sd0->layer[0][0].b_off), 2 * md.h + __ldg(&sd0->layer[0][2].Np), et);
     }
     const bool tr = (warp_e & 3) == 0;     // one tracing warp per group
@@ -633,8 +636,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           }
           e_pro += T2_CLOCK() - e_tmp;
           if (tr) T2_TRACE(73 + 40 * (g & 1));
-          for (int net = 0; net < md.nnets; ++net, ++units) {
-            const int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
+          for (int net = 0; net < nnets; ++net, ++units) {
+            const int act_kind = GA ? 1 : (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
             const float* bias_c = bias_s + (units & 1u) * bstride;           // staged by the previous pass
             const float* b1 = bias_c + g * 32;
             const float* bias = bias_c + 2 * md.h;
@@ -649,7 +652,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             // ---- staging for the NEXT pass, entirely off the critical path (a first-touch global load here, or in the
             //      chunk epilogues, would stall all four warps of a scheduler for an L2 round trip): the next step's scalars
             //      now; its tables and the next pass's biases once those scalars are visible (after layer 1, below) ----
-            if (net == 0 && sd_next != nullptr && et < 8) t2_stage_meta_async(sd_next, md.nnets, misc->meta[(stepc + 1) & 1u], et);
+            if (net == 0 && sd_next != nullptr && et < 8) t2_stage_meta_async(sd_next, nnets, misc->meta[(stepc + 1) & 1u], et);
             // ---- layer 1: chunk q in L1 slot q & 1 (128 columns, 32 per thread) -> act -> fp16 pairs written to the A1
             //      region [64 q, 64 q + 64) (normally a different TMEM region; see T2Geom::l1_even_inplace) ----
             for (int q = 0; q < NQ; ++q) {
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             // that depend on them (biases b1 | b2 | b3 of the next pass are contiguous in fblob)
             ptx::cp_async_wait_all();
             t2_epi_bar();
-            if (net + 1 < md.nnets) {
+            if (net + 1 < nnets) {
               t2_stage_bias_async(bias_s + ((units + 1) & 1u) * bstride, a.fblob + meta[5 + net + 1], 2 * md.h + meta[3 + net + 1], et);
             } else if (sd_next != nullptr) {
               const int* mn = misc->meta[(stepc + 1) & 1u];
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               ptx::tmem_ld16(lane_base + G.la_col + (uint32_t)c0, r);
               ptx::tmem_ld_wait();
               // every branch: gather the affected z2 columns first, store them last (see the gather above)
-              if (md.kind == GBNF_KIND_GLOW && md.coupling == GBNF_COUPLING_AFFINE) {
+              if (GA || (md.kind == GBNF_KIND_GLOW && md.coupling == GBNF_COUPLING_AFFINE)) {
                 const float2* bias2 = reinterpret_cast<const float2*>(bias);
                 float4 t[8];
                 float z[8];
@@ -876,9 +879,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
 #undef T2_CLOCK
 #undef T2_TRACE
 
-template <int T, int P, int Q>
+template <int T, int P, int Q, bool GA = false>
 inline cudaError_t tc2_configure_one() {
-  return cudaFuncSetAttribute(coupling_tc2_kernel<T, P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return cudaFuncSetAttribute(coupling_tc2_kernel<T, P, Q, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 inline cudaError_t tc2_configure() {
   cudaError_t e = cudaSuccess;
@@ -886,6 +889,8 @@ inline cudaError_t tc2_configure() {
   T2_CFG(0, 0, 0); T2_CFG(1, 0, 0); T2_CFG(0, 1, 0); T2_CFG(1, 1, 0); T2_CFG(0, 2, 0); T2_CFG(1, 2, 0);
   T2_CFG(0, 0, 4); T2_CFG(1, 0, 4); T2_CFG(0, 1, 4); T2_CFG(1, 1, 4); T2_CFG(0, 2, 4); T2_CFG(1, 2, 4);
   T2_CFG(0, 0, 2); T2_CFG(1, 0, 2);
+  if (e == cudaSuccess) e = tc2_configure_one<0, 0, 4, true>();
+  if (e == cudaSuccess) e = tc2_configure_one<1, 0, 4, true>();
 #undef T2_CFG
   return e;
 }
@@ -894,7 +899,10 @@ inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStre
 #define T2_GO(T, P, Q) coupling_tc2_kernel<T, P, Q><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p)
 #define T2_GO_Q(T, P) do { if (a.md.h == 512) T2_GO(T, P, 4); else T2_GO(T, P, 0); } while (0)
   // production builds of the two widths the BASELINE configurations use are specialised (h = 512: NQT = 4, h = 256: NQT = 2)
-#define T2_GO_PROD(T) do { if (a.md.h == 512) T2_GO(T, 0, 4); else if (a.md.h == 256) T2_GO(T, 0, 2); else T2_GO(T, 0, 0); } while (0)
+  const bool ga = a.md.kind == GBNF_KIND_GLOW && a.md.coupling == GBNF_COUPLING_AFFINE && a.md.act == GBNF_ACT_TANH && a.md.nnets == 1;
+#define T2_GO_PROD(T) do { \
+    if (a.md.h == 512 && ga) coupling_tc2_kernel<T, 0, 4, true><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p); \
+    else if (a.md.h == 512) T2_GO(T, 0, 4); else if (a.md.h == 256) T2_GO(T, 0, 2); else T2_GO(T, 0, 0); } while (0)
   if (p.tanh_mode == 0) { if (prof == 1) T2_GO_Q(0, 1); else if (prof == 2) T2_GO_Q(0, 2); else T2_GO_PROD(0); }
   else                  { if (prof == 1) T2_GO_Q(1, 1); else if (prof == 2) T2_GO_Q(1, 2); else T2_GO_PROD(1); }
 #undef T2_GO_PROD
