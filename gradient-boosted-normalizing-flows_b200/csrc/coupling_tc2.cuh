@@ -247,9 +247,10 @@ __device__ __forceinline__ void t2_stage_bias_async(float* dst, const float* src
 // NQT: h / 128 as a compile-time constant (0 = read it from the model): with a constant geometry the whole schedule unrolls
 // into straight-line code, which matters on the MMA-issuer warp where every dependent scalar instruction costs 4-6 cycles
 // that are NOT hidden whenever a stage is issue-bound (measured ~400 cycles of bookkeeping per stage in the generic form).
-// GA: the model is known at compile time to be Glow / affine coupling / tanh nets (one net per step): the other coupling
-// variants, activations and the two-net RealNVP control flow drop out of the instantiation.
-template <int TANH_MODE, int PROF, int NQT, bool GA = false>
+// MV: model variant known at compile time - 1 = Glow / affine coupling / tanh nets (one net per step), 2 = RealNVP with tanh
+// s- and t-nets (two nets per step), 0 = read everything from the model: the other coupling variants, activations and net
+// counts drop out of the instantiation.
+template <int TANH_MODE, int PROF, int NQT, int MV = 0>
 __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArgs a, TcPlan plan) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // PTX predicate registers that carry the result of an early mbarrier.test_wait across the MMA block issued in between
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
   asm volatile(".reg .pred t2_p_full;\n\t.reg .pred t2_p_sr;" ::);
   const ModelDims& md = a.md;
   const int D = md.D, Dv = md.Dv;
-  const int nnets = GA ? 1 : md.nnets;
+  const int nnets = MV == 1 ? 1 : MV == 2 ? 2 : md.nnets;
   float* zs = reinterpret_cast<float*>(smem + plan.off_zs);
   unsigned char* A0 = smem + plan.off_a0;
   float* xs = reinterpret_cast<float*>(smem + plan.off_a1);
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           e_pro += T2_CLOCK() - e_tmp;
           if (tr) T2_TRACE(73 + 40 * (g & 1));
           for (int net = 0; net < nnets; ++net, ++units) {
-            const int act_kind = GA ? 1 : (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
+            const int act_kind = MV ? 1 : (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
             const float* bias_c = bias_s + (units & 1u) * bstride;           // staged by the previous pass
             const float* b1 = bias_c + g * 32;
             const float* bias = bias_c + 2 * md.h;
@@ -752,7 +753,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               ptx::tmem_ld16(lane_base + G.la_col + (uint32_t)c0, r);
               ptx::tmem_ld_wait();
               // every branch: gather the affected z2 columns first, store them last (see the gather above)
-              if (GA || (md.kind == GBNF_KIND_GLOW && md.coupling == GBNF_COUPLING_AFFINE)) {
+              if (MV == 1 || (MV == 0 && md.kind == GBNF_KIND_GLOW && md.coupling == GBNF_COUPLING_AFFINE)) {
                 const float2* bias2 = reinterpret_cast<const float2*>(bias);
                 float4 t[8];
                 float z[8];
@@ -787,7 +788,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                     const int j = c0 + half * 8 + jj;
                     const float acc = __uint_as_float(r[half * 8 + jj]) + bias[j];
                     const float zn = (z[jj] + t[jj].x) * t[jj].y + t[jj].z;
-                    if (md.kind == GBNF_KIND_GLOW) {
+                    if (MV != 2 && md.kind == GBNF_KIND_GLOW) {
                       z[jj] = zn + acc;                                                 // additive coupling, glow.py:328-329
                     } else if (net == 0) {                                              // RealNVP t_net: keep the shift
                       if (j < out_dim) sh[row * plan.out_max + j] = acc;
@@ -797,7 +798,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                       lsum += (j < out_dim) ? acc : 0.f;                                // transformations.py:577
                     }
                   }
-                  if (md.kind == GBNF_KIND_GLOW || net == 1) {
+                  if ((MV != 2 && md.kind == GBNF_KIND_GLOW) || net == 1) {
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) if (c0 + half * 8 + jj < out_dim) zrow[__float_as_int(t[jj].w)] = z[jj];
                   }
@@ -879,9 +880,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
 #undef T2_CLOCK
 #undef T2_TRACE
 
-template <int T, int P, int Q, bool GA = false>
+template <int T, int P, int Q, int MV = 0>
 inline cudaError_t tc2_configure_one() {
-  return cudaFuncSetAttribute(coupling_tc2_kernel<T, P, Q, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return cudaFuncSetAttribute(coupling_tc2_kernel<T, P, Q, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 inline cudaError_t tc2_configure() {
   cudaError_t e = cudaSuccess;
@@ -889,8 +890,10 @@ inline cudaError_t tc2_configure() {
   T2_CFG(0, 0, 0); T2_CFG(1, 0, 0); T2_CFG(0, 1, 0); T2_CFG(1, 1, 0); T2_CFG(0, 2, 0); T2_CFG(1, 2, 0);
   T2_CFG(0, 0, 4); T2_CFG(1, 0, 4); T2_CFG(0, 1, 4); T2_CFG(1, 1, 4); T2_CFG(0, 2, 4); T2_CFG(1, 2, 4);
   T2_CFG(0, 0, 2); T2_CFG(1, 0, 2);
-  if (e == cudaSuccess) e = tc2_configure_one<0, 0, 4, true>();
-  if (e == cudaSuccess) e = tc2_configure_one<1, 0, 4, true>();
+  if (e == cudaSuccess) e = tc2_configure_one<0, 0, 4, 1>();
+  if (e == cudaSuccess) e = tc2_configure_one<1, 0, 4, 1>();
+  if (e == cudaSuccess) e = tc2_configure_one<0, 0, 2, 2>();
+  if (e == cudaSuccess) e = tc2_configure_one<1, 0, 2, 2>();
 #undef T2_CFG
   return e;
 }
@@ -899,9 +902,12 @@ inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStre
 #define T2_GO(T, P, Q) coupling_tc2_kernel<T, P, Q><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p)
 #define T2_GO_Q(T, P) do { if (a.md.h == 512) T2_GO(T, P, 4); else T2_GO(T, P, 0); } while (0)
   // production builds of the two widths the BASELINE configurations use are specialised (h = 512: NQT = 4, h = 256: NQT = 2)
+  // ... and so are the two model variants they use (Glow / affine / tanh at h = 512, RealNVP / tanh at h = 256)
   const bool ga = a.md.kind == GBNF_KIND_GLOW && a.md.coupling == GBNF_COUPLING_AFFINE && a.md.act == GBNF_ACT_TANH && a.md.nnets == 1;
+  const bool rn = a.md.kind == GBNF_KIND_REALNVP && a.md.act == GBNF_ACT_TANH && a.md.nnets == 2;
 #define T2_GO_PROD(T) do { \
-    if (a.md.h == 512 && ga) coupling_tc2_kernel<T, 0, 4, true><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p); \
+    if (a.md.h == 512 && ga) coupling_tc2_kernel<T, 0, 4, 1><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p); \
+    else if (a.md.h == 256 && rn) coupling_tc2_kernel<T, 0, 2, 2><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p); \
     else if (a.md.h == 512) T2_GO(T, 0, 4); else if (a.md.h == 256) T2_GO(T, 0, 2); else T2_GO(T, 0, 0); } while (0)
   if (p.tanh_mode == 0) { if (prof == 1) T2_GO_Q(0, 1); else if (prof == 2) T2_GO_Q(0, 2); else T2_GO_PROD(0); }
   else                  { if (prof == 1) T2_GO_Q(1, 1); else if (prof == 2) T2_GO_Q(1, 2); else T2_GO_PROD(1); }
