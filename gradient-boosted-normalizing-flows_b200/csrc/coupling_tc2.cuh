@@ -884,37 +884,45 @@ template <int T, int P, int Q, int MV = 0>
 inline cudaError_t tc2_configure_one() {
   return cudaFuncSetAttribute(coupling_tc2_kernel<T, P, Q, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
+// Instantiations.  Production (PROF = 0): geometry NQT in {4 (h = 512), 2 (h = 256), 0 (read from the model)} x model variant
+// MV in {0 generic, 1 Glow / affine / tanh, 2 RealNVP / tanh} x both tanh modes; profiling builds (PROF = 1, 2) only exist for the
+// generic variant and NQT in {0, 4}.
+#define T2_FOR_PROD(X) X(4, 0) X(2, 0) X(0, 0) X(4, 1) X(2, 1) X(0, 1) X(4, 2) X(2, 2) X(0, 2)
 inline cudaError_t tc2_configure() {
   cudaError_t e = cudaSuccess;
 #define T2_CFG(T, P, Q) if (e == cudaSuccess) e = tc2_configure_one<T, P, Q>()
-  T2_CFG(0, 0, 0); T2_CFG(1, 0, 0); T2_CFG(0, 1, 0); T2_CFG(1, 1, 0); T2_CFG(0, 2, 0); T2_CFG(1, 2, 0);
-  T2_CFG(0, 0, 4); T2_CFG(1, 0, 4); T2_CFG(0, 1, 4); T2_CFG(1, 1, 4); T2_CFG(0, 2, 4); T2_CFG(1, 2, 4);
-  T2_CFG(0, 0, 2); T2_CFG(1, 0, 2);
-  if (e == cudaSuccess) e = tc2_configure_one<0, 0, 4, 1>();
-  if (e == cudaSuccess) e = tc2_configure_one<1, 0, 4, 1>();
-  if (e == cudaSuccess) e = tc2_configure_one<0, 0, 2, 2>();
-  if (e == cudaSuccess) e = tc2_configure_one<1, 0, 2, 2>();
+  T2_CFG(0, 1, 0); T2_CFG(1, 1, 0); T2_CFG(0, 2, 0); T2_CFG(1, 2, 0);
+  T2_CFG(0, 1, 4); T2_CFG(1, 1, 4); T2_CFG(0, 2, 4); T2_CFG(1, 2, 4);
 #undef T2_CFG
+#define T2_CFG_PROD(Q, MV) if (e == cudaSuccess) e = tc2_configure_one<0, 0, Q, MV>(); if (e == cudaSuccess) e = tc2_configure_one<1, 0, Q, MV>();
+  T2_FOR_PROD(T2_CFG_PROD)
+#undef T2_CFG_PROD
   return e;
 }
 
 inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStream_t st, int prof) {
 #define T2_GO(T, P, Q) coupling_tc2_kernel<T, P, Q><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p)
 #define T2_GO_Q(T, P) do { if (a.md.h == 512) T2_GO(T, P, 4); else T2_GO(T, P, 0); } while (0)
-  // production builds of the two widths the BASELINE configurations use are specialised (h = 512: NQT = 4, h = 256: NQT = 2)
-  // ... and so are the two model variants they use (Glow / affine / tanh at h = 512, RealNVP / tanh at h = 256)
-  const bool ga = a.md.kind == GBNF_KIND_GLOW && a.md.coupling == GBNF_COUPLING_AFFINE && a.md.act == GBNF_ACT_TANH && a.md.nnets == 1;
-  const bool rn = a.md.kind == GBNF_KIND_REALNVP && a.md.act == GBNF_ACT_TANH && a.md.nnets == 2;
-#define T2_GO_PROD(T) do { \
-    if (a.md.h == 512 && ga) coupling_tc2_kernel<T, 0, 4, 1><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p); \
-    else if (a.md.h == 256 && rn) coupling_tc2_kernel<T, 0, 2, 2><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p); \
-    else if (a.md.h == 512) T2_GO(T, 0, 4); else if (a.md.h == 256) T2_GO(T, 0, 2); else T2_GO(T, 0, 0); } while (0)
-  if (p.tanh_mode == 0) { if (prof == 1) T2_GO_Q(0, 1); else if (prof == 2) T2_GO_Q(0, 2); else T2_GO_PROD(0); }
-  else                  { if (prof == 1) T2_GO_Q(1, 1); else if (prof == 2) T2_GO_Q(1, 2); else T2_GO_PROD(1); }
-#undef T2_GO_PROD
+  if (prof == 1 || prof == 2) {
+    if (p.tanh_mode == 0) { if (prof == 1) T2_GO_Q(0, 1); else T2_GO_Q(0, 2); }
+    else                  { if (prof == 1) T2_GO_Q(1, 1); else T2_GO_Q(1, 2); }
+    return 0;
+  }
 #undef T2_GO_Q
 #undef T2_GO
-  return 0;
+  const int q = (a.md.h == 512) ? 4 : (a.md.h == 256) ? 2 : 0;
+  const int mv = (a.md.kind == GBNF_KIND_GLOW && a.md.coupling == GBNF_COUPLING_AFFINE && a.md.act == GBNF_ACT_TANH && a.md.nnets == 1) ? 1
+               : (a.md.kind == GBNF_KIND_REALNVP && a.md.act == GBNF_ACT_TANH && a.md.nnets == 2) ? 2 : 0;
+#define T2_GO_PROD(Q, MV) \
+  if (q == Q && mv == MV) { \
+    if (p.tanh_mode == 0) coupling_tc2_kernel<0, 0, Q, MV><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p); \
+    else                  coupling_tc2_kernel<1, 0, Q, MV><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p); \
+    return 0; \
+  }
+  T2_FOR_PROD(T2_GO_PROD)
+#undef T2_GO_PROD
+  return -1;
 }
+#undef T2_FOR_PROD
 
 }  // namespace gbnf
