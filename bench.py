@@ -146,12 +146,118 @@ def cpu_port_throughput(cfg_name, rows, repeats=1):
     return rows / best, threads, best
 
 
+def _ref_harness():
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_harness
+    return ref_harness
+
+
+def cpu_baseline_leg(a):
+    """`cpu_baseline` of our arm's line: ~10-30 s of the reference's CPU path on the host cores (rank 0, N = 1)."""
+    rh = _ref_harness()
+    if rh.available():
+        import torch
+        ref = rh.load()
+        cfg = CONFIGS[a.config]
+        torch.set_num_threads(os.cpu_count())
+        g = torch.Generator().manual_seed(1234)
+        x_init = torch.randn((4096, cfg["D"]), generator=g)
+        model, args = rh.build_model(ref, cfg, "cpu", x_init)
+        rows = min(a.batch, 65536)
+        x = torch.randn((rows, cfg["D"]), generator=g)
+        rh.density_step(ref, model, x[:4096], args, toy=cfg["toy"])           # warm-up
+        t = time.perf_counter()
+        n = 0
+        while n == 0 or (time.perf_counter() - t < 10.0 and n < 8):
+            rh.density_step(ref, model, x, args, toy=cfg["toy"])
+            n += 1
+        secs = time.perf_counter() - t
+        return {"value": rows * n / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": f"{n} x {rows} rows of {a.config}, unmodified reference (baseline/_ref) on torch CPU, {secs:.1f} s"}
+    v, threads, secs = cpu_port_throughput(a.config, a.cpu_rows)
+    return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{a.cpu_rows} rows of {a.config} in 8192-row batches, {secs:.1f} s"}
+
+
+def run_reference_unmodified(a):
+    """--impl reference, preferred form: the UNMODIFIED reference (baseline/_ref, staged by baseline/vendor_reference.py) on the
+    host cores -- models.boosted_flow.BoostedFlow + the driver lines density_experiment.py:561-571 / :627-641 replayed by
+    baseline/ref_harness.density_step -- all host threads, same configuration and batch as our arm."""
+    import torch
+    rh = _ref_harness()
+    ref = rh.load()
+    cfg = CONFIGS[a.config]
+    torch.set_num_threads(os.cpu_count())
+    threads = torch.get_num_threads()
+    g = torch.Generator().manual_seed(1234)
+    x_init = torch.randn((4096, cfg["D"]), generator=g)
+    model, args = rh.build_model(ref, cfg, "cpu", x_init)
+    rows = a.batch
+    x = torch.randn((rows, cfg["D"]), generator=g)
+    # bounded sample: one probe step decides how many rows a step may take so that W + K steps end within ~3 minutes
+    t = time.perf_counter()
+    rh.density_step(ref, model, x[:8192], args, toy=cfg["toy"])
+    rate = min(rows, 8192) / (time.perf_counter() - t)
+    budget_rows = rate * 180.0 / (a.steps + a.warmup)
+    while rows > 1024 and rows > budget_rows:
+        rows //= 2
+    xb = x[:rows].contiguous()
+    for _ in range(a.warmup):
+        rh.density_step(ref, model, xb, args, toy=cfg["toy"])
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        G, w = rh.density_step(ref, model, xb, args, toy=cfg["toy"])
+    dt = time.perf_counter() - t0
+    val = rows * a.steps / dt
+    sample = (f"{rows} rows/step of {a.config}: unmodified reference BoostedFlow (baseline/_ref) + density_experiment.py:561-571,"
+              f"627-641, torch {torch.__version__} CPU, eval mode, no_grad")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "batch": rows, "same_config": rows == a.batch,
+                   "note": "unmodified reference modules from baseline/_ref on the host cores"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def gpu_torch_baseline(a, device, steps=5, warmup=2):
+    """The unmodified reference moved to the SAME B200 (`.cuda()`, stock eager PyTorch: ATen kernels + cuBLAS), same
+    configuration and batch, timed with CUDA events: the honest library-GPU baseline."""
+    import torch
+    rh = _ref_harness()
+    if not rh.available():
+        return {"value": None, "unavailable": "baseline/_ref is not staged (run baseline/vendor_reference.py where /root/reference exists)"}
+    ref = rh.load()
+    cfg = CONFIGS[a.config]
+    g = torch.Generator(device=device).manual_seed(1234)
+    x = torch.randn((a.batch, cfg["D"]), device=device, generator=g)
+    model, args = rh.build_model(ref, cfg, device, x[:4096])
+    for _ in range(warmup):
+        rh.density_step(ref, model, x, args, toy=cfg["toy"])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        rh.density_step(ref, model, x, args, toy=cfg["toy"])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model
+    torch.cuda.empty_cache()
+    return {"value": a.batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "dtype": "f32 (TF32 off: torch default)",
+            "what": f"unmodified reference BoostedFlow.cuda() + density_experiment.py:561-571,627-641, eager torch {torch.__version__}, batch {a.batch}"}
+
+
 def run_reference(a):
-    """--impl reference: the reference algorithm's CPU implementation (oracle port; the Python reference itself cannot
-    travel to the GPU box and has no compiled form) on all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on all host threads.  With baseline/_ref staged this
+    is the UNMODIFIED reference (run_reference_unmodified); otherwise the oracle's torch-CPU port stands in (kind = "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if not a.port and _ref_harness().available():
+        return run_reference_unmodified(a)
     cfg = CONFIGS[a.config]
     rows_per_step = min(a.batch, 8192)
     import numpy as np
@@ -258,6 +364,36 @@ def run_ours(a):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- N > 1: the sharded result must equal the single-GPU kernel path BEFORE anything is timed --------------------------
+    parity = None
+    if world > 1:
+        xb = batches[0]
+        if comp_par:     # every rank holds the same rows: component-parallel mixture vs the fused single-GPU launch
+            G_cp = gd.mixture_component_parallel(ops, xb[:8192].contiguous(), C)
+            G_1 = model.mixture_log_density(xb[:8192].contiguous(), C)
+            err = float(((G_cp - G_1).abs() / G_1.abs().clamp_min(1e-30)).max())
+            ok = err < 2e-6
+            parity = {"what": "component-parallel G_ll (all-gather + mixture kernel) vs the fused single-GPU launch, 8192 rows",
+                      "max_rel_err": err, "tol": 2e-6}
+        else:            # global-softmax weights of the row shards vs the single-GPU weight kernels on the gathered G_ll
+            G_loc = model.mixture_log_density(xb, C)
+            w_loc = gd.boosting_weights_batch_parallel(ops, G_loc, "density")
+            G_all = torch.empty(world * a.batch, device=device)
+            dist.all_gather_into_tensor(G_all, G_loc)
+            w_one = model.boosting_weights(G_all)[rank * a.batch:(rank + 1) * a.batch]
+            err = float(((w_loc - w_one).abs() / w_one.abs().clamp_min(1e-30)).max())
+            ok = err < 5e-6
+            parity = {"what": f"batch-parallel boosting weights ({world} shards x {a.batch} rows, global softmax) vs the "
+                              "single-GPU weight kernels on the all-gathered G_ll", "max_rel_err": err, "tol": 5e-6}
+        flag = torch.tensor([0 if ok else 1], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        errt = torch.tensor([err], device=device)
+        dist.all_reduce(errt, op=dist.ReduceOp.MAX)
+        parity["max_rel_err"] = errt.item()
+        parity["passed"] = flag.item() == 0
+        if not parity["passed"]:
+            raise SystemExit(f"multi-GPU parity check FAILED: {parity}")
+
     # ---- `value`: inputs resident in HBM ----------------------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
@@ -360,11 +496,11 @@ def run_ours(a):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.batch * D * 4, "d2h_bytes_per_step": a.batch * 8},
         "gpu_launches": launches,
     }
+    if parity is not None:
+        out["parity_check"] = parity
     if world == 1 and not a.no_cpu:
-        rows = a.cpu_rows
-        v, threads, secs = cpu_port_throughput(a.config, rows)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"{rows} rows of {a.config} in 8192-row batches, {secs:.1f} s"}
+        out["cpu_baseline"] = cpu_baseline_leg(a)
+        out["gpu_torch_baseline"] = gpu_torch_baseline(a, device)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -384,6 +520,7 @@ def main():
     p.add_argument("--rows", type=int, default=1 << 20)
     p.add_argument("--cpu-rows", type=int, default=524288)
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--port", action="store_true", help="--impl reference: time the oracle's torch-CPU port even when baseline/_ref exists")
     a = p.parse_args()
     a.warmup = max(a.warmup, 3)
     if CONFIGS[a.config]["h"] > 512 and a.mode != "fp32":

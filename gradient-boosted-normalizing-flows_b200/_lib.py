@@ -67,6 +67,7 @@ SIGNATURES = {
     "gbnf_actnorm_init": (C.c_int, [_vp, _i64, _i32, C.c_float, _vp, _vp, _vp]),
     "gbnf_sample_component": (C.c_int, [C.POINTER(_f32), _i32, _f64, _i32, C.POINTER(_i32)]),
     "gbnf_get_info": (C.c_int, [_vp, C.POINTER(Info)]),
+    "gbnf_check_status": (C.c_int, [_vp, _vp]),
     "gbnf_get_profile": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "gbnf_get_trace": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
 }

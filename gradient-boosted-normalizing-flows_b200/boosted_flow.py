@@ -61,6 +61,8 @@ class BoostedFlow(nn.Module):
         self.toy_base = bool(getattr(args, "toy_base", False))   # toy_experiment.py uses model.base_dist
         self._handle = None
         self._handle_device = None
+        self._handle_cfg = None
+        self._base_sig = None
         self._pack_sig = {}
         self._keepalive = {}
 
@@ -138,12 +140,17 @@ class BoostedFlow(nn.Module):
         cfg.device = device.index if device.index is not None else torch.cuda.current_device()
         return cfg
 
+    def _config_key(self):
+        a = self.args
+        return (self.component_type, self.z_size, a.h_size, a.num_flows, self.num_components, a.coupling_network_depth,
+                a.coupling_network, getattr(a, "flow_coupling", "affine"), self.toy_base, self.gemm_mode)
+
     def handle(self, device=None):
         device = torch.device(device) if device is not None else self.rho.device
         if device.type != "cuda":
             raise RuntimeError("the GBNF density path runs on CUDA only (there is no CPU fallback); move the model "
                                "and data to a B200")
-        if self._handle is not None and self._handle_device == device:
+        if self._handle is not None and self._handle_device == device and self._handle_cfg == self._config_key():
             return self._handle
         self.release()
         lib = _lib.load()
@@ -151,13 +158,28 @@ class BoostedFlow(nn.Module):
         cfg = self._config(device)
         _lib.check(lib.gbnf_create(C.byref(h), C.byref(cfg)))
         self._handle, self._handle_device = h, device
+        self._handle_cfg = self._config_key()
         self._pack_sig = {}
-        if self.toy_base:
-            self._keepalive["base"] = (self.base_dist_mean.detach().float().contiguous(),
-                                       self.base_dist_var.detach().float().contiguous())
-            m, s = self._keepalive["base"]
+        if self.toy_base:   # copied by the library (stream-ordered): nothing to keep alive
+            m = self.base_dist_mean.detach().to(device, torch.float32).contiguous()
+            s = self.base_dist_var.detach().to(device, torch.float32).contiguous()
             _lib.check(lib.gbnf_set_base(h, _ptr(m), _ptr(s), _stream(device)))
+            self._base_sig = self._base_signature()
         return h
+
+    def _base_signature(self):
+        return tuple((t.data_ptr(), t._version) for t in (self.base_dist_mean, self.base_dist_var))
+
+    def invalidate(self):
+        """Forget every packed component (call after writes the version counters cannot see: `.data` edits, load())."""
+        self._pack_sig = {}
+        self._base_sig = None
+
+    def check_status(self):
+        """Synchronise and raise GbnfError if a kernel reported a numeric problem (a value not finite in fp16) or a
+        watchdog timeout since the last check (gbnf_check_status)."""
+        if self._handle is not None:
+            _lib.check(_lib.load().gbnf_check_status(self._handle, _stream(self._handle_device)))
 
     def release(self):
         if self._handle is not None:
@@ -206,6 +228,13 @@ class BoostedFlow(nn.Module):
         """(Re)tile component c's parameters into the library's packed blob when they changed since the last pack."""
         device = self.rho.device
         h = self.handle(device)
+        if self.toy_base and getattr(self, "_base_sig", None) != self._base_signature():
+            # the toy base density lives in every component's pack: re-send it, which un-packs all components
+            m = self.base_dist_mean.detach().to(device, torch.float32).contiguous()
+            s = self.base_dist_var.detach().to(device, torch.float32).contiguous()
+            _lib.check(_lib.load().gbnf_set_base(h, _ptr(m), _ptr(s), _stream(device)))
+            self._base_sig = self._base_signature()
+            self._pack_sig = {}
         sig = self._signature(c)
         if not force and self._pack_sig.get(c) == sig:
             return

@@ -79,7 +79,9 @@ struct CouplingArgs {
   float* lse_terms;                // [num_tiles * 128][n_mix]
   unsigned int* tile_ctr;          // [num_tiles], zero between launches (reset by the last arriver)
   int exp_flags;                   // experiments (GBNF_EXP env, diagnostics only): bit 0 = producer skips the weight copies
-  int* error_flag;                 // device int, set non-zero on an internal timeout (f16 path)
+  int* error_flag;                 // status words in MAPPED HOST memory (the host can read them after a trap, without a
+                                   // synchronisation): [0] watchdog code of a timed-out wait, [1] fp16 weight overflow (pack),
+                                   // [2] a value entering an fp16 GEMM operand was not finite in fp16
   long long* prof;                 // optional cycle counters (CTA 0), see gbnf_get_profile
 };
 
@@ -127,7 +129,9 @@ struct OnlineLse {
     if (t > m) { s = s * expf(m - t) + 1.f; m = t; }
     else       { s += expf(t - m); }
   }
-  __device__ __forceinline__ float value() const { return (s > 0.f) ? m + logf(s) : 0.f; }
+  // torch.logsumexp semantics: no finite term -> -inf, a NaN term -> NaN, a +inf term -> +inf (the n_mix == 0 case
+  // "G_ll = zeros", density_experiment.py:612, is handled on the host with a memset and never reaches this)
+  __device__ __forceinline__ float value() const { return (s == 0.f) ? -INFINITY : m + logf(s); }
 };
 
 }  // namespace gbnf

@@ -116,7 +116,7 @@ __device__ __forceinline__ uint32_t a_chunk_off(int row, int k8) {
 // hidden layer epilogue: TMEM accumulator -> +bias -> act -> fp16 -> A1 (this thread's half of the columns)
 template <int ACT, int TANH_MODE>
 __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tbase, int quad, int row, int hsel, int Np,
-                                                   const float* __restrict__ bias, unsigned char* A1) {
+                                                   const float* __restrict__ bias, unsigned char* A1, int* status) {
   const int half = Np >> 1;
   const uint32_t lane_base = tbase + ((uint32_t)(quad * 32) << 16);
   for (int c0 = hsel * half; c0 < (hsel + 1) * half; c0 += 32) {
@@ -135,6 +135,8 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tbase, int quad, int
       const float v5 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 5]) + b1.y);
       const float v6 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 6]) + b1.z);
       const float v7 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 7]) + b1.w);
+      if (ACT == 2 && !(fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7))) <= 65504.f))
+        *reinterpret_cast<volatile int*>(status + 2) = 1;                           // ReLU activation not finite in fp16
       st_shared_v4(A1 + a_chunk_off(row, c0 + 8 * q), pack_half2(v0, v1), pack_half2(v2, v3), pack_half2(v4, v5),
                    pack_half2(v6, v7));
     }
@@ -300,6 +302,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc_kernel(CouplingArgs
               for (int e = 0; e < 8; ++e) {
                 const int j = ch * 8 + e;
                 v[e] = (j < sd.in_dim) ? zs[row * Dv + __ldg(idx1 + j)] : 0.f;
+                if (!(fabsf(v[e]) <= 65504.f)) *reinterpret_cast<volatile int*>(a.error_flag + 2) = 1;   // not finite in fp16
               }
               st_shared_v4(A0 + a_chunk_off(row, ch * 8), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
                            pack_half2(v[6], v[7]));
@@ -321,8 +324,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) coupling_tc_kernel(CouplingArgs
               e_tmp = clock64();
               const float* bias = a.fblob + L.b_off;
               if (l < md.nlayers - 1) {
-                if (act_kind == 1) tc_hidden_epilogue<1, TANH_MODE>(tbase, quad, row, hsel, L.Np, bias, A1);
-                else               tc_hidden_epilogue<2, TANH_MODE>(tbase, quad, row, hsel, L.Np, bias, A1);
+                if (act_kind == 1) tc_hidden_epilogue<1, TANH_MODE>(tbase, quad, row, hsel, L.Np, bias, A1, a.error_flag);
+                else               tc_hidden_epilogue<2, TANH_MODE>(tbase, quad, row, hsel, L.Np, bias, A1, a.error_flag);
                 e_hid += clock64() - e_tmp;
               } else {
                 // ---- last layer: coupling transform on this thread's 32-column slice ----

@@ -112,8 +112,15 @@ __device__ __forceinline__ void t2_quad_bar(int quad) { asm volatile("bar.sync %
 __device__ __forceinline__ void t2_epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // 16 accumulator values of one row -> bias + activation -> 8 packed fp16 pairs
+// (ReLU activations are unbounded: a value that is not finite in fp16 raises status word 2, see CouplingArgs::error_flag)
 template <int ACT, int TANH_MODE>
-__device__ __forceinline__ void t2_act_pack16(const uint32_t (&r)[16], const float* __restrict__ bias, uint32_t* p) {
+__device__ __forceinline__ void t2_act_pack16(const uint32_t (&r)[16], const float* __restrict__ bias, uint32_t* p, int* status) {
+  if (ACT == 2) {
+    float mx = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) mx = fmaxf(mx, __uint_as_float(r[q]) + bias[q]);
+    if (!(mx <= 65504.f)) *reinterpret_cast<volatile int*>(status + 2) = 1;
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);      // staged in shared memory (broadcast read)
@@ -125,7 +132,13 @@ __device__ __forceinline__ void t2_act_pack16(const uint32_t (&r)[16], const flo
 }
 // 32 accumulator values of one row -> bias + activation -> 16 packed fp16 pairs
 template <int ACT, int TANH_MODE>
-__device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const float* __restrict__ bias, uint32_t* p) {
+__device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const float* __restrict__ bias, uint32_t* p, int* status) {
+  if (ACT == 2) {
+    float mx = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(r[q]) + bias[q]);
+    if (!(mx <= 65504.f)) *reinterpret_cast<volatile int*>(status + 2) = 1;
+  }
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
@@ -631,6 +644,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               for (int e = 0; e < 8; ++e) if (ch * 8 + e < in_dim) zrow[__float_as_int(t[e].w)] = v[e];   // never write the scratch column
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = (ch * 8 + e < in_dim) ? v[e] : 0.f;
+              {   // a value that fp16 cannot hold (|v| > 65504, inf, NaN) would silently become inf / NaN in the GEMM operand
+                const float mx = fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))),
+                                       fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7]))));
+                if (!(mx <= 65504.f)) *reinterpret_cast<volatile int*>(a.error_flag + 2) = 1;
+              }
               st_shared_v4(A0 + a_chunk_off(row, ch * 8), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
                            pack_half2(v[6], v[7]));
             }
@@ -669,8 +687,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                 ptx::tmem_ld32(lane_base + G.l1_col[q & 1] + (uint32_t)g * 32u, r);
                 ptx::tmem_ld_wait();
                 if (PROF && warp_e == 0 && q == 1) T2_TRACE(120);
-                if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, b1 + q * kT2Chunk, p);
-                else               t2_act_pack32<2, TANH_MODE>(r, b1 + q * kT2Chunk, p);
+                if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, b1 + q * kT2Chunk, p, a.error_flag);
+                else               t2_act_pack32<2, TANH_MODE>(r, b1 + q * kT2Chunk, p, a.error_flag);
                 if (PROF && warp_e == 0 && q == 1) T2_TRACE(121);
               }
               if (G.l1_even_inplace && !(q & 1)) t2_quad_bar(quad);   // packed quarter may overlap the row's unread accumulator
@@ -717,8 +735,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                   uint32_t r[32];
                   ptx::tmem_ld32(sc + (uint32_t)g * 32u, r);
                   ptx::tmem_ld_wait();
-                  if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, bj + g * 32, p);
-                  else               t2_act_pack32<2, TANH_MODE>(r, bj + g * 32, p);
+                  if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, bj + g * 32, p, a.error_flag);
+                  else               t2_act_pack32<2, TANH_MODE>(r, bj + g * 32, p, a.error_flag);
                 }
                 t2_quad_bar(quad);             // all four threads of the row have read their columns
                 ptx::tmem_st16(sc + (uint32_t)g * 16u, p);
@@ -728,8 +746,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                   uint32_t r[16];
                   ptx::tmem_ld16(sc + (uint32_t)g * 16u, r);
                   ptx::tmem_ld_wait();
-                  if (act_kind == 1) t2_act_pack16<1, TANH_MODE>(r, bj + g * 16, p);
-                  else               t2_act_pack16<2, TANH_MODE>(r, bj + g * 16, p);
+                  if (act_kind == 1) t2_act_pack16<1, TANH_MODE>(r, bj + g * 16, p, a.error_flag);
+                  else               t2_act_pack16<2, TANH_MODE>(r, bj + g * 16, p, a.error_flag);
                 }
                 ptx::tmem_st8(sc + (uint32_t)g * 16u, p);
               }
@@ -859,7 +877,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           for (int i = 0; i < a.n_mix; ++i) M = fmaxf(M, __ldcg(tv + i));
           float S = 0.f;
           for (int i = 0; i < a.n_mix; ++i) { const float t = __ldcg(tv + i); if (t != -INFINITY) S += expf(t - M); }
-          a.G_ll[gr] = (S > 0.f) ? M + logf(S) : 0.f;
+          // torch.logsumexp semantics: a NaN term -> NaN (fmaxf drops it, the sum does not), all -inf -> -inf, +inf -> +inf
+          a.G_ll[gr] = (M == INFINITY) ? INFINITY : (S == 0.f) ? -INFINITY : M + logf(S);
         }
       }
     }

@@ -33,6 +33,19 @@ int fail(int code, const std::string& msg) {
       return fail(GBNF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
   } while (0)
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it (a single-process
+// multi-GPU PyTorch program must not have its current device changed behind its back).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
 
@@ -51,8 +64,9 @@ struct gbnf_ctx {
   int* iblob = nullptr;
   void* wblob = nullptr;
   long long f_count = 0, i_count = 0, w_bytes = 0, cc_off = 0;
-  const float* base_mean = nullptr;
-  const float* base_scale = nullptr;
+  float* base_mean = nullptr;    // handle-owned copies of the toy base density vectors [D] (gbnf_set_base)
+  float* base_scale = nullptr;
+  bool base_set = false;
   gbnf_step_params* step_params_d = nullptr;
   // workspace
   float* partial = nullptr;      // [max_grid][2]
@@ -63,7 +77,8 @@ struct gbnf_ctx {
   double* tile_sums = nullptr;   // [cap_tiles]
   double* tile_offs = nullptr;   // [cap_tiles + 1]
   long long cum_cap = 0;
-  int* flags = nullptr;          // [0] kernel error flag, [1] fp16 overflow flag
+  int* flags_host = nullptr;     // status words in mapped pinned host memory: [0] watchdog code of a timed-out in-kernel wait,
+  int* flags = nullptr;          // [1] fp16 weight overflow (pack), [2] non-finite fp16 GEMM operand; `flags` = device alias
   float* lse_part = nullptr;     // pipelined kernel: per-row mixture terms coef_c + log q_c (reduced by the last unit of a tile)
   unsigned int* tile_ctr = nullptr;
   long long lse_cap = 0, ctr_cap = 0;
@@ -79,6 +94,53 @@ struct gbnf_ctx {
 };
 
 namespace {
+
+const char* watchdog_text(int code) {
+  switch (code) {
+    case 10: return "TMA producer waiting for a free ring stage";
+    case 11: return "TMA producer waiting for a free last-layer weight buffer";
+    case 20: return "MMA issuer waiting for the A0 operand";
+    case 21: return "MMA issuer waiting for a weight stage";
+    case 22: return "MMA issuer waiting for an A1 quarter";
+    case 23: return "MMA issuer waiting for a packed A2 piece";
+    case 24: return "MMA issuer waiting for last-layer weights";
+    case 30: return "epilogue waiting for a layer-1 accumulator";
+    case 31: return "epilogue waiting for a layer-2 accumulator";
+    case 32: return "epilogue waiting for the last-layer accumulator";
+    default: return "in-kernel wait";
+  }
+}
+// Status words the kernels leave in mapped host memory (readable without a synchronisation, and after a trap).  Called at the
+// top of every entry point: an error raised by an EARLIER launch is reported by the first call that sees it.
+int check_status(gbnf_ctx* h) {
+  if (!h->flags_host) return GBNF_OK;
+  volatile int* f = h->flags_host;
+  if (f[0] != 0) {
+    const int code = f[0];
+    return fail(GBNF_ERR_CUDA, "kernel watchdog: a bounded wait timed out (code " + std::to_string(code) + ": " + watchdog_text(code) +
+                                   "); the kernel trapped and the CUDA context is unusable");
+  }
+  if (f[2] != 0) {
+    f[2] = 0;
+    return fail(GBNF_ERR_NUMERIC, "an input or activation of an earlier launch was not finite in fp16 (|v| > 65504, inf or NaN): its "
+                                  "results are invalid; standardise the data or use GBNF_GEMM_FP32");
+  }
+  return GBNF_OK;
+}
+int cuda_fail(gbnf_ctx* h, const char* what, cudaError_t e) {
+  std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+  if (h && h->flags_host && h->flags_host[0] != 0)
+    msg += " [kernel watchdog code " + std::to_string(h->flags_host[0]) + ": " + watchdog_text(h->flags_host[0]) + "]";
+  return fail(GBNF_ERR_CUDA, msg);
+}
+#define CUDA_TRY_H(h, expr)                                              \
+  do {                                                                   \
+    cudaError_t e_ = (expr);                                             \
+    if (e_ != cudaSuccess) return cuda_fail((h), #expr, e_);             \
+  } while (0)
+#define ENTER(h)                                                         \
+  DeviceGuard guard_((h)->cfg.device);                                   \
+  do { int rc_ = check_status(h); if (rc_ != GBNF_OK) return rc_; } while (0)
 
 int plan_layout(gbnf_ctx* h) {
   const gbnf_config& c = h->cfg;
@@ -259,7 +321,7 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
     if (rc != 0) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: launch configuration rejected");
   }
   h->launches++;
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }
 
@@ -287,7 +349,7 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   if (e != cudaSuccess || ndev == 0)
     return fail(GBNF_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
   if (c.device < 0 || c.device >= ndev) return fail(GBNF_ERR_INVALID, "bad device ordinal");
-  CUDA_TRY(cudaSetDevice(c.device));
+  DeviceGuard guard_(c.device);
   cudaDeviceProp prop{};
   CUDA_TRY(cudaGetDeviceProperties(&prop, c.device));
   if (prop.major < 10) return fail(GBNF_ERR_CUDA, "device is not sm_100-class (kernels are built for sm_100a only)");
@@ -316,8 +378,13 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   CREATE_TRY(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
   CREATE_TRY(cudaMalloc(&h->ms, 2 * sizeof(float)));
   CREATE_TRY(cudaMalloc(&h->wsum, sizeof(double)));
-  CREATE_TRY(cudaMalloc(&h->flags, 2 * sizeof(int)));
-  CREATE_TRY(cudaMemset(h->flags, 0, 2 * sizeof(int)));
+  CREATE_TRY(cudaHostAlloc((void**)&h->flags_host, 4 * sizeof(int), cudaHostAllocMapped));
+  std::memset(h->flags_host, 0, 4 * sizeof(int));
+  CREATE_TRY(cudaHostGetDevicePointer((void**)&h->flags, h->flags_host, 0));
+  if (c.base == GBNF_BASE_DIAG_NORMAL) {
+    CREATE_TRY(cudaMalloc(&h->base_mean, (size_t)c.D * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->base_scale, (size_t)c.D * sizeof(float)));
+  }
   CREATE_TRY(cudaMalloc(&h->prof, 288 * sizeof(long long)));
   CREATE_TRY(cudaMemset(h->prof, 0, 288 * sizeof(long long)));
   CREATE_TRY(cudaMemcpy(h->comps_d, h->comps_h.data(), h->comps_h.size() * sizeof(CompDesc), cudaMemcpyHostToDevice));
@@ -338,20 +405,26 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
 
 void gbnf_destroy(gbnf_handle h) {
   if (!h) return;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard_(h->cfg.device);
+  cudaFree(h->base_mean); cudaFree(h->base_scale);
+  if (h->flags_host) cudaFreeHost(h->flags_host);
+  h->flags_host = nullptr; h->flags = nullptr;
   cudaFree(h->steps_d); cudaFree(h->comps_d); cudaFree(h->fblob); cudaFree(h->iblob); cudaFree(h->wblob);
   cudaFree(h->step_params_d); cudaFree(h->partial); cudaFree(h->ticket); cudaFree(h->ms); cudaFree(h->wsum);
   cudaFree(h->lse_part); cudaFree(h->tile_ctr);
-  cudaFree(h->cum); cudaFree(h->tile_sums); cudaFree(h->tile_offs); cudaFree(h->flags); cudaFree(h->prof);
+  cudaFree(h->cum); cudaFree(h->tile_sums); cudaFree(h->tile_offs); cudaFree(h->prof);
   delete h;
 }
 
 int gbnf_set_base(gbnf_handle h, const float* d_mean, const float* d_scale, void* stream) {
-  (void)stream;
   if (!h) return fail(GBNF_ERR_INVALID, "null handle");
   if (h->cfg.base != GBNF_BASE_DIAG_NORMAL) return fail(GBNF_ERR_INVALID, "handle was not created with GBNF_BASE_DIAG_NORMAL");
   if (!d_mean || !d_scale) return fail(GBNF_ERR_INVALID, "null base pointers");
-  h->base_mean = d_mean; h->base_scale = d_scale;
+  ENTER(h);
+  // copied (stream-ordered): the caller's tensors are only borrowed for the duration of the call
+  CUDA_TRY_H(h, cudaMemcpyAsync(h->base_mean, d_mean, (size_t)h->cfg.D * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  CUDA_TRY_H(h, cudaMemcpyAsync(h->base_scale, d_scale, (size_t)h->cfg.D * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  h->base_set = true;
   std::fill(h->packed.begin(), h->packed.end(), 0);   // base constants live in each component's pack
   return GBNF_OK;
 }
@@ -362,9 +435,9 @@ int gbnf_pack_component(gbnf_handle h, int32_t c, const gbnf_component_params* p
   if (p->n_steps != h->cfg.K) return fail(GBNF_ERR_INVALID, "n_steps != K");
   if (h->cfg.kind == GBNF_KIND_REALNVP && p->flip_init != c)
     return fail(GBNF_ERR_INVALID, "RealNVP component c must have flip_init == c (models/boosted_flow.py:46)");
-  if (h->cfg.base == GBNF_BASE_DIAG_NORMAL && !h->base_mean) return fail(GBNF_ERR_STATE, "call gbnf_set_base first");
+  if (h->cfg.base == GBNF_BASE_DIAG_NORMAL && !h->base_set) return fail(GBNF_ERR_STATE, "call gbnf_set_base first");
   cudaStream_t st = (cudaStream_t)stream;
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   const ModelDims& md = h->md;
   const bool f16 = (h->cfg.gemm_mode != GBNF_GEMM_FP32);
   StepDesc* sd_h = &h->steps_h[(size_t)c * md.K];
@@ -404,13 +477,11 @@ int gbnf_pack_component(gbnf_handle h, int32_t c, const gbnf_component_params* p
         h->launches++;
       }
   }
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY_H(h, cudaGetLastError());
   if (f16) {
-    int ovf = 0;
-    CUDA_TRY(cudaMemcpyAsync(&ovf, h->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (ovf) {
-      CUDA_TRY(cudaMemsetAsync(h->flags + 1, 0, sizeof(int), st));
+    CUDA_TRY_H(h, cudaStreamSynchronize(st));          // documented in gbnf.h: the one entry point that synchronises
+    if (h->flags_host[1]) {
+      h->flags_host[1] = 0;
       return fail(GBNF_ERR_NUMERIC, "a weight is not finite in fp16; use GBNF_GEMM_FP32 for this model");
     }
   }
@@ -426,7 +497,7 @@ int gbnf_component_logq(gbnf_handle h, const float* d_x, int64_t B, int32_t c0, 
   if (B == 0) return GBNF_OK;   // empty batch: nothing to do (pointers of empty tensors may be NULL)
   if (!d_x) return fail(GBNF_ERR_INVALID, "null x");
   if (!d_logq && !d_z_opt && !d_ldj_opt) return fail(GBNF_ERR_INVALID, "no output requested");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   return launch_coupling(h, d_x, B, c0, c1, d_logq, c1 - c0, d_z_opt, d_ldj_opt, nullptr, 0, -1, 0, nullptr,
                          (cudaStream_t)stream);
 }
@@ -441,11 +512,11 @@ int gbnf_mixture_logdensity(gbnf_handle h, const float* d_logq, int64_t B, int32
     return fail(GBNF_ERR_INVALID, "the geometric mixture (utils/density_plotting.py:199-226) takes >= 1 component and no skip_c");
   if (B == 0) return GBNF_OK;
   if (!d_G_ll || (n_comp > 0 && (!d_logq || !d_rho))) return fail(GBNF_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   mixture_lse_kernel<<<grid_for(h, B, kMixThreads), kMixThreads, 0, (cudaStream_t)stream>>>(d_logq, B, ld, n_comp, d_rho,
                                                                                          skip_c, mix_mode, d_G_ll);
   h->launches++;
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }
 
@@ -459,7 +530,7 @@ int gbnf_fused_eval(gbnf_handle h, const float* d_x, int64_t B, int32_t n_comp, 
                                   "on materialised log q: gbnf_component_logq + gbnf_mixture_logdensity)");
   if (B == 0) return GBNF_OK;
   if (!d_G_ll) return fail(GBNF_ERR_INVALID, "null G_ll");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   if (n_comp == 0) {   // G_ll = zeros, density_experiment.py:612
     CUDA_TRY(cudaMemsetAsync(d_G_ll, 0, (size_t)B * sizeof(float), (cudaStream_t)stream));
     return GBNF_OK;
@@ -471,11 +542,11 @@ int gbnf_fused_eval(gbnf_handle h, const float* d_x, int64_t B, int32_t n_comp, 
 
 int gbnf_weight_stats(gbnf_handle h, const float* d_G_ll, int64_t B, float* d_ms, void* stream) {
   if (!h || !d_G_ll || !d_ms || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   softmax_stats_kernel<<<grid_for(h, B, kMixThreads * 4), kMixThreads, 0, (cudaStream_t)stream>>>(d_G_ll, B, h->partial,
                                                                                               h->ticket, d_ms);
   h->launches++;
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }
 
@@ -483,23 +554,23 @@ int gbnf_weight_apply(gbnf_handle h, const float* d_G_ll, int64_t B, const float
                       int32_t mode, float* d_w, double* d_wsum, void* stream) {
   (void)mode;
   if (!h || !d_G_ll || !d_ms || !d_w || !d_wsum || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   zero_double_kernel<<<1, 1, 0, st>>>(d_wsum);
   weight_apply_kernel<<<grid_for(h, B, kMixThreads * 4), kMixThreads, 0, st>>>(d_G_ll, B, d_ms, clamp_lo, clamp_hi, d_w,
                                                                              d_wsum, nullptr);
   h->launches += 2;
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }
 
 int gbnf_weight_renorm(gbnf_handle h, float* d_w, int64_t B, const double* d_wsum, int32_t mode, void* stream) {
   if (!h || !d_w || !d_wsum || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   weight_renorm_kernel<<<grid_for(h, B, kMixThreads * 4), kMixThreads, 0, (cudaStream_t)stream>>>(
       d_w, B, d_wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, nullptr);
   h->launches++;
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }
 
@@ -507,7 +578,7 @@ int gbnf_boost_weights(gbnf_handle h, const float* d_G_ll, int64_t B, float clam
                        float* d_w, float* d_stats, void* stream) {
   if (!h || !d_G_ll || !d_w || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
   if (mode != GBNF_WEIGHTS_DENSITY && mode != GBNF_WEIGHTS_TOY) return fail(GBNF_ERR_INVALID, "bad weights mode");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   const int g = grid_for(h, B, kMixThreads * 4);
   softmax_stats_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->partial, h->ticket, h->ms);
@@ -515,7 +586,7 @@ int gbnf_boost_weights(gbnf_handle h, const float* d_G_ll, int64_t B, float clam
   weight_apply_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->ms, clamp_lo, clamp_hi, d_w, h->wsum, d_stats);
   weight_renorm_kernel<<<g, kMixThreads, 0, st>>>(d_w, B, h->wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, d_stats);
   h->launches += 4;
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }
 
@@ -523,7 +594,7 @@ int gbnf_resample(gbnf_handle h, const float* d_w, int64_t B, const double* d_u,
   if (!h || !d_w || B <= 0 || n < 0) return fail(GBNF_ERR_INVALID, "bad argument");
   if (n == 0) return GBNF_OK;
   if (!d_u || !d_idx) return fail(GBNF_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   int rc = ensure_scan_workspace(h, B);
   if (rc != GBNF_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -533,7 +604,7 @@ int gbnf_resample(gbnf_handle h, const float* d_w, int64_t B, const double* d_u,
   scan_finalize_kernel<<<tiles, kScanThreads, 0, st>>>(d_w, B, h->tile_offs, tiles, h->cum);
   resample_search_kernel<<<grid_for(h, n, kMixThreads), kMixThreads, 0, st>>>(h->cum, B, d_u, n, (long long*)d_idx);
   h->launches += 4;
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }
 
@@ -541,11 +612,11 @@ int gbnf_gather_rows(gbnf_handle h, const float* d_x, int32_t D, const int64_t* 
   if (!h || D <= 0 || n < 0) return fail(GBNF_ERR_INVALID, "bad argument");
   if (n == 0) return GBNF_OK;
   if (!d_x || !d_idx || !d_out) return fail(GBNF_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   gather_rows_kernel<<<grid_for(h, n * 32, kMixThreads), kMixThreads, 0, (cudaStream_t)stream>>>(
       d_x, D, (const long long*)d_idx, n, d_out);
   h->launches++;
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }
 
@@ -588,16 +659,24 @@ int gbnf_sample_component(const float* rho_host, int32_t n, double u, int32_t ex
   return GBNF_OK;
 }
 
+int gbnf_check_status(gbnf_handle h, void* stream) {
+  if (!h) return fail(GBNF_ERR_INVALID, "null handle");
+  DeviceGuard guard_(h->cfg.device);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(h, "cudaStreamSynchronize", e);
+  return check_status(h);
+}
+
 int gbnf_get_profile(gbnf_handle h, int64_t* out32) {
   if (!h || !out32) return fail(GBNF_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   CUDA_TRY(cudaMemcpy(out32, h->prof, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
   return GBNF_OK;
 }
 
 int gbnf_get_trace(gbnf_handle h, int64_t* out256) {
   if (!h || !out256) return fail(GBNF_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   CUDA_TRY(cudaMemcpy(out256, h->prof + 32, 256 * sizeof(long long), cudaMemcpyDeviceToHost));
   return GBNF_OK;
 }

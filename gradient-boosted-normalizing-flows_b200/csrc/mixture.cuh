@@ -19,7 +19,7 @@ __device__ __forceinline__ float mixture_row_lse(const float4 (&v)[NV], int n, c
   float sum = 0.f;
 #pragma unroll
   for (int c = 0; c < 4 * NV; ++c) sum += __expf(t[c] - m);                // exp(-inf) = 0 for skipped / padded terms
-  return (m == -INFINITY) ? 0.f : m + __logf(sum);
+  return (m == -INFINITY) ? -INFINITY : m + __logf(sum);   // all terms -inf -> -inf; NaN propagates (torch.logsumexp)
 }
 // R rows in flight per thread (all their 128-bit loads are issued before the first logsumexp): the kernel is a pure stream,
 // what it needs is bytes in flight

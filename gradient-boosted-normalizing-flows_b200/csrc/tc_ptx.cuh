@@ -52,7 +52,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > kWaitLimitCycles) {
-      if (err_flag) atomicExch(err_flag, code);
+      if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = code;   // mapped host memory: survives the trap
       __threadfence_system();
       __trap();
     }

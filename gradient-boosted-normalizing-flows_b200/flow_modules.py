@@ -70,13 +70,13 @@ class ActNorm1d(nn.Module):
             with torch.cuda.device(x.device):
                 _lib.check(_lib.load().gbnf_actnorm_init(x.data_ptr(), x.shape[0], x.shape[1], float(self.scale), bias.data_ptr(),
                                                          logs.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream))
-            self.bias.data.copy_(bias.view(1, -1))
-            self.logs.data.copy_(logs.view(1, -1))
+            self.bias.copy_(bias.view(1, -1))       # in-place under no_grad: bumps the version counter the pack cache keys on
+            self.logs.copy_(logs.view(1, -1))
         else:   # CPU tensors (host-side tests): the reference's own formula
             shift = -sample.mean(dim=0, keepdim=True)
             second = ((sample + shift) ** 2).mean(dim=0, keepdim=True)
-            self.bias.data.copy_(shift)
-            self.logs.data.copy_(torch.log(self.scale / (second.sqrt() + 1e-6)))
+            self.bias.copy_(shift)
+            self.logs.copy_(torch.log(self.scale / (second.sqrt() + 1e-6)))
         self.inited = True
 
     def forward(self, x, logdet):

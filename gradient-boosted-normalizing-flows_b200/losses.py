@@ -57,6 +57,7 @@ def compute_kl_pq_loss(model, x, args, generator=None, return_aux=False):
         losses = {"nll": torch.mean(g_nll), "g_nll": torch.mean(g_nll)}
         losses["G_nll"] = torch.zeros_like(losses["g_nll"])
     if torch.isnan(losses["nll"]).any():
+        model.check_status()      # a value that fp16 could not hold raises GbnfError(GBNF_ERR_NUMERIC) with the cause
         raise ValueError(f"Nan Encountered. nll={losses['nll']}, x={x}, losses={losses}")
     return (losses, aux) if return_aux else losses
 

@@ -11,7 +11,15 @@
  *     caller owns (PyTorch tensors in practice) and that is only BORROWED for the duration of the call;
  *   - all tensors are contiguous row-major, float32 unless stated; indices are int64;
  *   - every launch goes on the caller's stream (`stream` is a cudaStream_t passed as void*); no entry point
- *     synchronises the device unless documented;
+ *     synchronises unless documented (gbnf_pack_component in the f16 modes, gbnf_check_status, the diagnostics);
+ *   - every entry point runs on the handle's device and restores the caller's current device before returning;
+ *   - the kernels report through three status words in mapped host memory, read (without a synchronisation) at the
+ *     top of every entry point: an in-kernel watchdog timeout (GBNF_ERR_CUDA, with the code of the wait that
+ *     timed out) or a value that fp16 cannot hold entering a tensor-core GEMM operand (GBNF_ERR_NUMERIC) is
+ *     reported by the first call made after the offending launch finished; gbnf_check_status() synchronises the
+ *     stream and reports at once;
+ *   - fp16 tensor-core modes: inputs, activations and weights must be finite in fp16 (|v| <= 65504); density data
+ *     is standardised upstream (utils/miniboone.py:57-65), raw data should use GBNF_GEMM_FP32;
  *   - every entry returns 0 on success or a negative gbnf_status; gbnf_last_error() gives the text
  *     (thread-local); no C++ exception crosses the boundary;
  *   - one handle per device; calls on one handle are not re-entrant;
@@ -36,7 +44,7 @@ typedef enum {
   GBNF_ERR_INVALID = -1, /* bad argument / unsupported configuration */
   GBNF_ERR_CUDA = -2,    /* CUDA runtime error (text in gbnf_last_error) */
   GBNF_ERR_STATE = -3,   /* e.g. component not packed yet */
-  GBNF_ERR_NUMERIC = -4  /* weights not representable in the selected GEMM operand type */
+  GBNF_ERR_NUMERIC = -4  /* weights / inputs / activations not representable in the selected GEMM operand type */
 } gbnf_status;
 
 enum { GBNF_KIND_REALNVP = 0, GBNF_KIND_GLOW = 1 };              /* models/boosted_flow.py:44-50 */
@@ -104,12 +112,14 @@ void gbnf_destroy(gbnf_handle h);
 const char* gbnf_last_error(void);
 int gbnf_abi_version(void);
 
-/* Re-tile one component's parameters into the handle's packed blob (device -> device, async on `stream`).
+/* Re-tile one component's parameters into the handle's packed blob (device -> device, on `stream`).
  * Call after construction, after every load() (utils/utilities.py:42-75) and whenever a component's
- * parameters changed before it is evaluated as a fixed component. */
+ * parameters changed before it is evaluated as a fixed component.  In the f16 modes this call SYNCHRONISES the
+ * stream (it reads the fp16 weight-overflow word and returns GBNF_ERR_NUMERIC when a weight is not finite in fp16). */
 int gbnf_pack_component(gbnf_handle h, int32_t c, const gbnf_component_params* p, void* stream);
 
-/* Toy path base density Normal(mean[D], scale[D]) (models/generative_flow.py:22-23,38-42). Device pointers. */
+/* Toy path base density Normal(mean[D], scale[D]) (models/generative_flow.py:22-23,38-42). Device pointers; the
+ * vectors are COPIED (stream-ordered), the caller's tensors are not referenced after the call. */
 int gbnf_set_base(gbnf_handle h, const float* d_mean, const float* d_scale, void* stream);
 
 /* ---- the hot path ----------------------------------------------------------------------------------- */
@@ -187,6 +197,10 @@ typedef struct {
   int32_t reserved;
 } gbnf_info;
 int gbnf_get_info(gbnf_handle h, gbnf_info* out);
+
+/* Synchronises `stream` and returns the status the kernels left (GBNF_OK, GBNF_ERR_NUMERIC, or GBNF_ERR_CUDA with the
+ * watchdog code in gbnf_last_error).  The drop-in's NaN guard (density_experiment.py:671-672) calls this. */
+int gbnf_check_status(gbnf_handle h, void* stream);
 
 /* Cycle counters of CTA 0 of the last tensor-core coupling launch (synchronises the device; diagnostics only):
  * [0..7] MMA warp: total, wait a_ready, wait weights, issue; [8..15] epilogue thread 0: total, wait accumulator,

@@ -11,4 +11,10 @@ CONFIGS = {
     "glow_d43_h256": (dict(kind="glow", D=43, C=2, K=2, h=256), 6, 160, False),
     "realnvp_d6_h128_bn": (dict(kind="realnvp", D=6, C=2, K=3, h=128, batch_norm=True), 7, 150, False),
     "toy_d2": (dict(kind="realnvp", D=2, C=8, K=1, h=64, rho_init="uniform"), 5, 100, True),
+    # the HEADLINE instantiation of the pipelined kernel (h = 512: tight TMEM geometry, 128 / 64-column layer-2 chunks) and a
+    # depth-2 coupling network (serial tensor-core kernel), both pinned against the reference itself
+    "glow_d43_h512": (dict(kind="glow", D=43, C=2, K=2, h=512), 8, 160, False),
+    "glow_d43_h128_depth2": (dict(kind="glow", D=43, C=2, K=2, h=128, coupling_network_depth=2), 9, 150, False),
 }
+# fixtures whose initial state_dict is stored as per-tensor SHA-1 digests instead of values (file size)
+STATE0_DIGEST_ONLY = {"glow_d43_h512"}

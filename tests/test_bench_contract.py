@@ -42,8 +42,28 @@ def test_reference_arm_prints_one_contract_line():
               "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    staged = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "models", "boosted_flow.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_port_fallback():
+    """Without the staged reference (or with --port) the arm times the oracle's torch-CPU port and says so."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--port", "--config", "cfg1_toy",
+                          "--steps", "1", "--warmup", "1", "--batch", "256"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+def test_staged_reference_matches_its_source():
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("the reference tree only exists in the build container")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "vendor_reference.py"), "--check"], capture_output=True,
+                         text=True)
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref")):
+        pytest.skip("baseline/_ref not staged yet (python __graft_entry__.py build stages it)")
+    assert out.returncode == 0, out.stdout + out.stderr
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -301,6 +301,41 @@ def test_baseline_configs_vs_oracle(cfg, mode):
         model.release()
 
 
+_BENCH_REF = {}
+
+
+def _bench_batch_reference(cfg, B):
+    """fp64 oracle log q of the bench batch, computed once per configuration (about a minute of host time for cfg4)."""
+    if cfg not in _BENCH_REF:
+        md, x = _synthetic(cfg, B)
+        m64 = orc.cast_model(md, np.float64)
+        _BENCH_REF[cfg] = np.concatenate([orc.all_component_logq(m64, x[s:s + 8192].astype(np.float64)) for s in range(0, B, 8192)], 0)
+    return _BENCH_REF[cfg]
+
+
+@pytest.mark.parametrize("mode", ["f16", "f16fast"])
+@pytest.mark.parametrize("cfg", ["cfg3_miniboone", "cfg4_hepmass"])
+def test_bench_batch_vs_oracle(cfg, mode):
+    """bench.py's own step -- 65 536 rows through the production instantiation coupling_tc2_kernel<*, 0, 4, 1> -- against the
+    fp64 oracle on EVERY row, at the north-star gate (1e-4 relative on per-sample log q and G_ll)."""
+    B = 65536
+    md, x = _synthetic(cfg, B)
+    model = build_model(md, "cuda", gemm_mode=mode)
+    try:
+        G, lq = model.mixture_log_density(dev(x), md["C"], return_logq=True)
+        model.check_status()
+        inf = model.info()
+        assert inf["pipelined"] == 1 and inf["grid"] == inf["num_sms"]
+        ref = _bench_batch_reference(cfg, B)
+        close(lq.cpu().numpy(), ref, mode, md["kind"])
+        close(G.cpu().numpy(), orc.mixture_recursion(ref, md["rho"].astype(np.float64), md["C"]), mode, md["kind"])
+        # and the boosting weights of that batch (global softmax over 65 536 rows)
+        w = model.boosting_weights(G)
+        np.testing.assert_allclose(w.cpu().numpy(), orc.boost_weights(G.cpu().numpy()), rtol=5e-6, atol=1e-12)
+    finally:
+        model.release()
+
+
 # ---- size-independent properties at full batch sizes ------------------------------------------------------------
 @pytest.mark.parametrize("mode", MODES)
 def test_properties_full_batch(mode):
