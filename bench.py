@@ -523,10 +523,6 @@ def main():
     p.add_argument("--port", action="store_true", help="--impl reference: time the oracle's torch-CPU port even when baseline/_ref exists")
     a = p.parse_args()
     a.warmup = max(a.warmup, 3)
-    if CONFIGS[a.config]["h"] > 512 and a.mode != "fp32":
-        # no tensor-core kernel for h > 512 yet: the library refuses the f16 modes there, so say it and measure fp32
-        print(f"# {a.config}: h = {CONFIGS[a.config]['h']} has no tensor-core path yet, running --mode fp32", file=sys.stderr)
-        a.mode = "fp32"
     if a.impl == "reference":
         run_reference(a)
     else:

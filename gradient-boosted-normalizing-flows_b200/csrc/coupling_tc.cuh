@@ -99,6 +99,12 @@ template <int ACT, int TANH_MODE>   // ACT: 1 tanh, 2 relu
 __device__ __forceinline__ float tc_act(float v) {
   return ACT == 1 ? tc_tanh<TANH_MODE>(v) : fmaxf(v, 0.f);
 }
+// NaN-propagating maximum (fmaxf returns the non-NaN operand): used by the "finite in fp16" checks
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -135,7 +141,7 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tbase, int quad, int
       const float v5 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 5]) + b1.y);
       const float v6 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 6]) + b1.z);
       const float v7 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 7]) + b1.w);
-      if (ACT == 2 && !(fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7))) <= 65504.f))
+      if (ACT == 2 && !(fmax_nan(fmax_nan(fmax_nan(v0, v1), fmax_nan(v2, v3)), fmax_nan(fmax_nan(v4, v5), fmax_nan(v6, v7))) <= 65504.f))
         *reinterpret_cast<volatile int*>(status + 2) = 1;                           // ReLU activation not finite in fp16
       st_shared_v4(A1 + a_chunk_off(row, c0 + 8 * q), pack_half2(v0, v1), pack_half2(v2, v3), pack_half2(v4, v5),
                    pack_half2(v6, v7));

@@ -118,7 +118,7 @@ __device__ __forceinline__ void t2_act_pack16(const uint32_t (&r)[16], const flo
   if (ACT == 2) {
     float mx = 0.f;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) mx = fmaxf(mx, __uint_as_float(r[q]) + bias[q]);
+    for (int q = 0; q < 16; ++q) mx = fmax_nan(mx, __uint_as_float(r[q]) + bias[q]);
     if (!(mx <= 65504.f)) *reinterpret_cast<volatile int*>(status + 2) = 1;
   }
 #pragma unroll
@@ -136,7 +136,7 @@ __device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const flo
   if (ACT == 2) {
     float mx = 0.f;
 #pragma unroll
-    for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(r[q]) + bias[q]);
+    for (int q = 0; q < 32; ++q) mx = fmax_nan(mx, __uint_as_float(r[q]) + bias[q]);
     if (!(mx <= 65504.f)) *reinterpret_cast<volatile int*>(status + 2) = 1;
   }
 #pragma unroll
@@ -645,8 +645,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = (ch * 8 + e < in_dim) ? v[e] : 0.f;
               {   // a value that fp16 cannot hold (|v| > 65504, inf, NaN) would silently become inf / NaN in the GEMM operand
-                const float mx = fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))),
-                                       fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7]))));
+                const float mx = fmax_nan(fmax_nan(fmax_nan(fabsf(v[0]), fabsf(v[1])), fmax_nan(fabsf(v[2]), fabsf(v[3]))),
+                                          fmax_nan(fmax_nan(fabsf(v[4]), fabsf(v[5])), fmax_nan(fabsf(v[6]), fabsf(v[7]))));
                 if (!(mx <= 65504.f)) *reinterpret_cast<volatile int*>(a.error_flag + 2) = 1;
               }
               st_shared_v4(A0 + a_chunk_off(row, ch * 8), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
@@ -874,11 +874,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
         if (last && g == 0 && gr < a.B) {
           const float* tv = a.lse_terms + ((long long)tile * kTcRows + row) * a.n_mix;
           float M = -INFINITY;
-          for (int i = 0; i < a.n_mix; ++i) M = fmaxf(M, __ldcg(tv + i));
+          bool has_nan = false;
+          for (int i = 0; i < a.n_mix; ++i) { const float t = __ldcg(tv + i); M = fmaxf(M, t); has_nan |= (t != t); }
           float S = 0.f;
           for (int i = 0; i < a.n_mix; ++i) { const float t = __ldcg(tv + i); if (t != -INFINITY) S += expf(t - M); }
-          // torch.logsumexp semantics: a NaN term -> NaN (fmaxf drops it, the sum does not), all -inf -> -inf, +inf -> +inf
-          a.G_ll[gr] = (M == INFINITY) ? INFINITY : (S == 0.f) ? -INFINITY : M + logf(S);
+          // torch.logsumexp semantics: a NaN term -> NaN (fmaxf drops it), +inf -> +inf, all terms -inf -> -inf
+          a.G_ll[gr] = has_nan ? __int_as_float(0x7fc00000) : (M == INFINITY || M == -INFINITY) ? M : M + logf(S);
         }
       }
     }

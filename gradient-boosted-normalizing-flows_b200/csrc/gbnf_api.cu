@@ -15,6 +15,7 @@
 #include "coupling_fp32.cuh"
 #include "coupling_tc.cuh"
 #include "coupling_tc2.cuh"
+#include "coupling_tc3.cuh"
 
 using namespace gbnf;
 
@@ -88,6 +89,7 @@ struct gbnf_ctx {
   size_t smem_bytes = 0;
   TcPlan tc{};
   bool tc2 = false;              // pipelined tensor-core kernel (coupling_tc2.cuh) selected
+  bool tc3 = false;              // CTA-pair tensor-core kernel for h = 1024 (coupling_tc3.cuh) selected
   int profiling = 0;             // GBNF_PROF=1: cycle counters + event trace, 2: event trace only (gbnf_get_profile / _trace)
   int last_grid = 0;
   long long launches = 0;
@@ -213,8 +215,11 @@ int plan_layout(gbnf_ctx* h) {
     // pipelined kernel when the shape allows it (GBNF_TC_V1=1 forces the serial kernel, for A/B measurements)
     const char* force_v1 = std::getenv("GBNF_TC_V1");
     h->tc2 = tc2_eligible(md, h->steps_h) && !(force_v1 && force_v1[0] == '1');
+    h->tc3 = !h->tc2 && tc3_eligible(md, h->steps_h);
     std::string why;
-    if (h->tc2) {
+    if (h->tc3) {
+      if (!tc3_make_plan(md, h->steps_h, &h->tc)) return fail(GBNF_ERR_INVALID, "f16 tensor-core path (h = 1024): shared memory budget exceeded");
+    } else if (h->tc2) {
       if (!tc2_make_plan(md, h->steps_h, &h->tc)) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: shared memory budget exceeded");
       for (StepDesc& sd : h->steps_h)
         for (int net = 0; net < md.nnets; ++net) {
@@ -280,14 +285,15 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
   const int R = h->rows_per_cta;
   a.num_tiles = (int)((B + R - 1) / R);
   a.split = 1; a.comps_per_unit = c1 - c0; a.num_units = a.num_tiles;
-  if (h->cfg.gemm_mode != GBNF_GEMM_FP32 && h->tc2) {
+  const int workers = h->tc3 ? h->num_sms / 2 : h->num_sms;      // CTAs, or CTA pairs, that run concurrently
+  if (h->cfg.gemm_mode != GBNF_GEMM_FP32 && (h->tc2 || h->tc3)) {
     // split every tile's components over S units when that shortens the critical CTA (waves x components per unit)
     const int ncomp = c1 - c0;
     long long best = -1;
     for (int S = 1; S <= ncomp; S *= 2) {
       const int cpu = (ncomp + S - 1) / S;
       const int units = a.num_tiles * ((ncomp + cpu - 1) / cpu);
-      const long long cost = (long long)((units + h->num_sms - 1) / h->num_sms) * cpu;
+      const long long cost = (long long)((units + workers - 1) / workers) * cpu;
       if (best < 0 || cost < best) { best = cost; a.comps_per_unit = cpu; a.split = (ncomp + cpu - 1) / cpu; }
     }
     a.num_units = a.num_tiles * a.split;
@@ -310,14 +316,14 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
       a.lse_terms = h->lse_part; a.tile_ctr = h->tile_ctr;
     }
   }
-  const int grid = std::min(a.num_units, h->num_sms);
-  h->last_grid = grid;
+  const int grid = std::min(a.num_units, workers);
+  h->last_grid = h->tc3 ? 2 * grid : grid;
   if (h->cfg.gemm_mode == GBNF_GEMM_FP32) {
     if (R == 64) coupling_fp32_kernel<64><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
     else if (R == 32) coupling_fp32_kernel<32><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
     else coupling_fp32_kernel<16><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
   } else {
-    int rc = h->tc2 ? tc2_launch(a, h->tc, grid, st, h->profiling) : tc_launch(a, h->tc, grid, st);
+    int rc = h->tc3 ? tc3_launch(a, h->tc, grid, st) : h->tc2 ? tc2_launch(a, h->tc, grid, st, h->profiling) : tc_launch(a, h->tc, grid, st);
     if (rc != 0) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: launch configuration rejected");
   }
   h->launches++;
@@ -397,6 +403,7 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   } else {
     CREATE_TRY(tc_configure(h->tc));
     CREATE_TRY(tc2_configure());
+    CREATE_TRY(tc3_configure());
   }
 #undef CREATE_TRY
   *out = h;
@@ -470,7 +477,9 @@ int gbnf_pack_component(gbnf_handle h, int32_t c, const gbnf_component_params* p
         const LayerDesc& L = sd_h[k].layer[net][l];
         const long long total = (long long)L.Kp * L.Np;
         const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8);
-        if (f16)
+        if (f16 && h->tc3)
+          pack_weight_tc3_kernel<<<grid, 256, 0, st>>>(sp.W[net][l], sp.b[net][l], L, l, (__half*)h->wblob, h->fblob, h->flags + 1);
+        else if (f16)
           pack_weight_f16_kernel<<<grid, 256, 0, st>>>(sp.W[net][l], sp.b[net][l], L, (__half*)h->wblob, h->fblob, h->flags + 1);
         else
           pack_weight_fp32_kernel<<<grid, 256, 0, st>>>(sp.W[net][l], sp.b[net][l], L, (float*)h->wblob, h->fblob);
@@ -513,6 +522,10 @@ int gbnf_mixture_logdensity(gbnf_handle h, const float* d_logq, int64_t B, int32
   if (B == 0) return GBNF_OK;
   if (!d_G_ll || (n_comp > 0 && (!d_logq || !d_rho))) return fail(GBNF_ERR_INVALID, "null pointer");
   ENTER(h);
+  if (n_comp == 0) {   // G_ll = zeros, density_experiment.py:612
+    CUDA_TRY_H(h, cudaMemsetAsync(d_G_ll, 0, (size_t)B * sizeof(float), (cudaStream_t)stream));
+    return GBNF_OK;
+  }
   mixture_lse_kernel<<<grid_for(h, B, kMixThreads), kMixThreads, 0, (cudaStream_t)stream>>>(d_logq, B, ld, n_comp, d_rho,
                                                                                          skip_c, mix_mode, d_G_ll);
   h->launches++;
@@ -691,7 +704,7 @@ int gbnf_get_info(gbnf_handle h, gbnf_info* out) {
   out->grid = h->last_grid;
   out->packed_bytes = h->w_bytes + h->f_count * 4 + h->i_count * 4;
   out->launches = h->launches;
-  out->pipelined = h->tc2 ? 1 : 0;
+  out->pipelined = h->tc3 ? 2 : h->tc2 ? 1 : 0;
   out->reserved = 0;
   return GBNF_OK;
 }

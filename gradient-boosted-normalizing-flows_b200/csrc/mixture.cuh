@@ -14,12 +14,15 @@ __device__ __forceinline__ float mixture_row_lse(const float4 (&v)[NV], int n, c
 #pragma unroll
   for (int i = 0; i < NV; ++i) { t[4 * i] = v[i].x; t[4 * i + 1] = v[i].y; t[4 * i + 2] = v[i].z; t[4 * i + 3] = v[i].w; }
   float m = -INFINITY;
+  bool has_nan = false;
 #pragma unroll
-  for (int c = 0; c < 4 * NV; ++c) { t[c] = (c < n) ? t[c] + coef[c] : -INFINITY; m = fmaxf(m, t[c]); }
+  for (int c = 0; c < 4 * NV; ++c) { t[c] = (c < n) ? t[c] + coef[c] : -INFINITY; m = fmaxf(m, t[c]); has_nan |= (t[c] != t[c]); }
   float sum = 0.f;
 #pragma unroll
   for (int c = 0; c < 4 * NV; ++c) sum += __expf(t[c] - m);                // exp(-inf) = 0 for skipped / padded terms
-  return (m == -INFINITY) ? -INFINITY : m + __logf(sum);   // all terms -inf -> -inf; NaN propagates (torch.logsumexp)
+  // torch.logsumexp: a NaN term -> NaN (fmaxf drops it), +inf -> +inf, all terms -inf -> -inf
+  if (has_nan) return __int_as_float(0x7fc00000);
+  return (m == INFINITY || m == -INFINITY) ? m : m + __logf(sum);
 }
 // R rows in flight per thread (all their 128-bit loads are issued before the first logsumexp): the kernel is a pure stream,
 // what it needs is bytes in flight

@@ -193,7 +193,8 @@ typedef struct {
   int32_t grid;            /* CTAs launched by the last coupling launch */
   int64_t packed_bytes;    /* size of the packed parameter blob */
   int64_t launches;        /* kernels launched through this handle so far */
-  int32_t pipelined;       /* 1: chunk-pipelined tensor-core kernel (coupling_tc2.cuh), 0: serial / fp32 kernel */
+  int32_t pipelined;       /* 2: CTA-pair tensor-core kernel for h = 1024 (coupling_tc3.cuh), 1: chunk-pipelined tensor-core
+                              kernel (coupling_tc2.cuh), 0: serial tensor-core / fp32 kernel */
   int32_t reserved;
 } gbnf_info;
 int gbnf_get_info(gbnf_handle h, gbnf_info* out);

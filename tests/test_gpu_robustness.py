@@ -49,7 +49,7 @@ def test_nan_input_row_gives_nan_density_not_density_one(mode):
     model, md = _model(mode)
     try:
         x = torch.randn(300, md["D"], device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
-        x[17, 2] = float("nan")
+        x[17, :] = float("nan")
         G, lq = model.mixture_log_density(x, md["C"], return_logq=True)
         assert torch.isnan(G[17]) and torch.isnan(lq[17]).all(), (G[17], lq[17])
         ok = torch.ones(300, dtype=torch.bool, device="cuda"); ok[17] = False
