@@ -118,8 +118,54 @@ class BoostedFlow(nn.Module):
         zeros = x.new_zeros((x.shape[0], self.z_size))
         return z, zeros, zeros.clone(), ldj, None
 
+    @torch.no_grad()
     def decode(self, z, y_onehot, temperature, components):
-        raise NotImplementedError("sampling / inverse path is outside this build's hot-path scope (SURVEY 8f.3)")
+        """x = flows[c]^{-1}(z) for ONE component c (models/boosted_flow.py:209-218; upstream's `y_onhot` keyword typo is not
+        reproduced).  z = None draws sample_size rows from the prior N(0, (exp(0) * temperature)^2) as Glow.decode /
+        RealNVPFlow.decode do (models/glow.py:114-116, models/realnvp.py:99-101)."""
+        c = self._sample_component(components) if isinstance(components, str) else components
+        if z is None:
+            t = 1.0 if temperature is None else float(temperature)
+            z = torch.normal(torch.zeros(self.flows[c].sample_size, self.z_size, device=self.rho.device),
+                             torch.ones(self.flows[c].sample_size, self.z_size, device=self.rho.device) * t)
+        return self.component_inverse(z, c)[0]
+
+    @torch.no_grad()
+    def component_inverse(self, z, c):
+        """(x, log-det of the inverse map) of component c through gbnf_component_inverse."""
+        z = _f32c(z)
+        self.pack_component(c)
+        x = torch.empty_like(z)
+        ldj = torch.empty(z.shape[0], device=z.device, dtype=torch.float32)
+        _lib.check(_lib.load().gbnf_component_inverse(self.handle(z.device), _ptr(z), z.shape[0], c, _ptr(x), _ptr(ldj),
+                                                      _stream(z.device)))
+        return x, ldj
+
+    @torch.no_grad()
+    def assign_components(self, u, n=None, exclude=-1):
+        """Per-sample component ids for mixture sampling: j_i = #{k : cum_k < u_i}, cum = cumsum_fp64(rho[:n]) / sum -- the
+        inverse-CDF contract of SURVEY 8c, bit-exact for given float64 uniforms (same kernel as the batch resampling)."""
+        n = (self.num_components if self.all_trained else self.component + 1) if n is None else n
+        p = self.rho[:n].detach().to(u.device, torch.float32).clone()
+        if exclude >= 0:
+            p[exclude] = 0.0
+        return self.resample(p.contiguous(), u)
+
+    @torch.no_grad()
+    def sample(self, n, u=None, z=None, temperature=1.0, generator=None):
+        """n draws from the boosted mixture G = sum_c rho_c q_c: every sample gets its OWN component (upstream's TODO at
+        models/boosted_flow.py:210-213), z ~ N(0, temperature^2), x = f_c^{-1}(z).  Returns (x, component ids)."""
+        dev = self.rho.device
+        if u is None:
+            u = torch.rand(n, dtype=torch.float64, device=dev, generator=generator)
+        if z is None:
+            z = torch.randn((n, self.z_size), device=dev, generator=generator) * float(temperature)
+        comp = self.assign_components(u)
+        x = torch.empty_like(z)
+        for c in torch.unique(comp).tolist():
+            rows = torch.nonzero(comp == c, as_tuple=False).squeeze(1)
+            x[rows] = self.component_inverse(z[rows].contiguous(), int(c))[0]
+        return x, comp
 
     def forward(self, x=None, y_onehot=None, z=None, temperature=None, components=None, reverse=False):
         if reverse:

@@ -38,7 +38,8 @@ struct StepDesc {
   long long idx_off;     // iblob: idx1[in_dim] | idx2[out_dim]  physical columns of z1 / z2
   // Branch-free tables of the pipelined tensor-core kernel, in GATHER order and padded to kEpPad entries:
   //   fblob @ ep_off  : float4 {add, mul, off, column as int bits}[kEpPad] in z1 order, then the same in z2 order
-  //                     (16-byte aligned); padding has mul = 0 (yields 0) and points at the scratch column D
+  //                     (16-byte aligned); padding has mul = 0 (yields 0) and points at the scratch column D; then the two
+  //                     tables of the INVERSE affine {-off, 1 / mul, -add, column}[kEpPad] (sampling direction)
   long long ep_off;
   long long eidx_off;
   LayerDesc layer[2][GBNF_MAX_LAYERS];   // net 0: glow block / realnvp t_net; net 1: realnvp s_net

@@ -245,4 +245,103 @@ __global__ void __launch_bounds__(kF32Threads, 1) coupling_fp32_kernel(CouplingA
   }
 }
 
+// ---- inverse direction (sampling): x = f_c^{-1}(z) for ONE component -------------------------------------------------------
+// Exact inverse of the forward kernel above, step by step in reverse order: coupling^-1 (the MLPs see z1, which the forward
+// step left untouched), then ActNorm^-1 / eval-BatchNorm^-1 on all columns.  Upstream: FlowStep.decode models/glow.py:344-366,
+// RealNVPFlow.decode models/realnvp.py:97-113 (whose flip pairing is not an inverse of encode, SURVEY 7 -- this one is).
+// a.x = z [B, D] (logical column order), a.z_out = x [B, D], a.ldj_out = log-det of the inverse map (= -forward log-det).
+template <int R>
+__global__ void __launch_bounds__(kF32Threads, 1) coupling_fp32_inverse_kernel(CouplingArgs a, int ld, int out_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ModelDims& md = a.md;
+  const int D = md.D, Dv = md.Dv;
+  float* zs = reinterpret_cast<float*>(smem_raw);
+  float* act0 = zs + ((R * Dv + 3) & ~3);
+  float* act1 = act0 + R * ld;
+  float* Ws = act1 + R * ld;
+  float* sh = Ws + 2 * kF32KT * kF32NT;
+  float* coef = sh + R * out_max;
+  float* ldj = coef + kMaxComponents;   // [R]
+  const int tid = threadIdx.x;
+  const int c = a.c0;
+  const CompDesc& cd = a.comps[c];
+  const int* sig = a.iblob + cd.sigma_off;
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const long long row0 = (long long)tile * R;
+    // z arrives in the flow's OUTPUT column order: logical column j lives at physical column sigma[j]
+    for (int i = tid; i < R * D; i += kF32Threads) {
+      int r = i / D, j = i % D;
+      long long gr = row0 + r;
+      zs[r * Dv + sig[j]] = (gr < a.B) ? a.x[gr * D + j] : 0.f;
+    }
+    if (tid < R) ldj[tid] = 0.f;
+    __syncthreads();
+    for (int k = md.K - 1; k >= 0; --k) {
+      const StepDesc& sd = a.steps[c * md.K + k];
+      const float* add = a.fblob + sd.vec_off;
+      const float* mul = add + Dv;
+      const float* off = mul + Dv;
+      const int* idx1 = a.iblob + sd.idx_off;
+      const int* idx2 = idx1 + sd.in_dim;
+      const int Kp0 = sd.layer[0][0].Kp;
+      for (int net = 0; net < md.nnets; ++net) {
+        for (int i = tid; i < R * Kp0; i += kF32Threads) {
+          int r = i / Kp0, j = i % Kp0;
+          act0[r * ld + j] = (j < sd.in_dim) ? zs[r * Dv + idx1[j]] : 0.f;
+        }
+        __syncthreads();
+        int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
+        run_net_fp32<R>(sd, net, act_kind, md.nlayers, a, act0, act1, ld, Ws);
+        if (md.nnets == 2 && net == 0) {
+          for (int i = tid; i < R * sd.out_dim; i += kF32Threads) {
+            int r = i / sd.out_dim, j = i % sd.out_dim;
+            sh[r * out_max + j] = act1[r * ld + j];
+          }
+          __syncthreads();
+        }
+      }
+      if (tid < R) {
+        const int r = tid;
+        float l = ldj[r];
+        if (md.kind == GBNF_KIND_GLOW) {
+          if (md.coupling == GBNF_COUPLING_AFFINE) {
+            for (int j = 0; j < sd.out_dim; ++j) {
+              float shift = act1[r * ld + 2 * j], raw = act1[r * ld + 2 * j + 1];
+              float s = 1.f / (1.f + expf(-(raw + 2.f)));
+              float* zp = zs + r * Dv + idx2[j];
+              *zp = *zp / s - shift;                                   // glow.py:354-356
+              l -= logf(s);                                            // glow.py:357
+            }
+          } else {
+            for (int j = 0; j < sd.out_dim; ++j) zs[r * Dv + idx2[j]] -= act1[r * ld + j];   // glow.py:350
+          }
+        } else {
+          for (int j = 0; j < sd.out_dim; ++j) {
+            float shift = sh[r * out_max + j], sc = act1[r * ld + j];
+            float* zp = zs + r * Dv + idx2[j];
+            *zp = (*zp - shift) * expf(-sc);                           // inverse of transformations.py:575
+            l -= sc;
+          }
+        }
+        ldj[r] = l;
+      }
+      __syncthreads();
+      if (sd.has_affine) {                                             // ActNorm reverse (layers.py:505-518) / BatchNorm^-1
+        for (int i = tid; i < R * D; i += kF32Threads) {
+          int r = i / D, p = i % D;
+          zs[r * Dv + p] = (zs[r * Dv + p] - off[p]) / mul[p] - add[p];
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = tid; i < R * D; i += kF32Threads) {
+      int r = i / D, p = i % D;
+      long long gr = row0 + r;
+      if (gr < a.B && a.z_out) a.z_out[gr * D + p] = zs[r * Dv + p];   // physical == logical at the flow's input
+    }
+    if (tid < R && a.ldj_out && row0 + tid < a.B) a.ldj_out[row0 + tid] = ldj[tid] - a.fblob[cd.const_off];
+    __syncthreads();
+  }
+}
+
 }  // namespace gbnf

@@ -263,7 +263,12 @@ __device__ __forceinline__ void t2_stage_bias_async(float* dst, const float* src
 // MV: model variant known at compile time - 1 = Glow / affine coupling / tanh nets (one net per step), 2 = RealNVP with tanh
 // s- and t-nets (two nets per step), 0 = read everything from the model: the other coupling variants, activations and net
 // counts drop out of the instantiation.
-template <int TANH_MODE, int PROF, int NQT, int MV = 0>
+// INV: 1 = inverse direction (sampling): a.x = z in the flow's output column order, ONE component (c0), steps walked from the
+// last to the first; every pass runs the same MLP(s) on z1 (which the forward step left untouched), un-does the coupling on
+// z2 and un-does the ActNorm / BatchNorm affine through the INVERSE gather-order tables (pack_meta_kernel); writes
+// a.z_out = x and a.ldj_out = log-det of the inverse map.  Upstream: FlowStep.decode models/glow.py:344-366,
+// RealNVPFlow.decode models/realnvp.py:97-113.
+template <int TANH_MODE, int PROF, int NQT, int MV = 0, int INV = 0>
 __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArgs a, TcPlan plan) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // PTX predicate registers that carry the result of an early mbarrier.test_wait across the MMA block issued in between
@@ -331,7 +336,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
       const int cb = a.c0 + (u % a.split) * a.comps_per_unit, ce = min(a.c1, cb + a.comps_per_unit);
       for (int c = cb; c < ce; ++c)
-        for (int k = 0; k < md.K; ++k) {
+        for (int kk = 0; kk < md.K; ++kk) {
+          const int k = INV ? md.K - 1 - kk : kk;
           const StepDesc* sd = a.steps + (c * md.K + k);
           for (int net = 0; net < nnets; ++net) {
             const int k0s = __ldg(&sd->layer[net][0].Kp) >> 4;
@@ -415,7 +421,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
       const int cb = a.c0 + (u % a.split) * a.comps_per_unit, ce = min(a.c1, cb + a.comps_per_unit);
       for (int c = cb; c < ce; ++c)
-        for (int k = 0; k < md.K; ++k) {
+        for (int kk = 0; kk < md.K; ++kk) {
+          const int k = INV ? md.K - 1 - kk : kk;
           const StepDesc* sd = a.steps + (c * md.K + k);
           for (int net = 0; net < nnets; ++net, ++units) {
             const int k0s = __ldg(&sd->layer[net][0].Kp) >> 4;
@@ -560,8 +567,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
     // (cp.async issued while this pass waits for the tensor core, completed and published at the end of the pass)
     if (blockIdx.x < a.num_units) {
       const int cb0 = a.c0 + ((int)blockIdx.x % a.split) * a.comps_per_unit;
-      const StepDesc* sd0 = a.steps + cb0 * md.K;
-      if (et < 2 * kEpPad) ptx::cp_async16(tab_s + et, reinterpret_cast<const float4*>(a.fblob + __ldg(&sd0->ep_off)) + et);
+      const StepDesc* sd0 = a.steps + cb0 * md.K + (INV ? md.K - 1 : 0);
+      if (et < 2 * kEpPad) ptx::cp_async16(tab_s + et, reinterpret_cast<const float4*>(a.fblob + __ldg(&sd0->ep_off)) + (INV ? 2 * kEpPad : 0) + et);
       if (et == 0) t2_stage_meta(sd0, nnets, misc->meta[0]);
       t2_stage_bias_async(bias_s, a.fblob + __ldg(&sd0->layer[0][0].b_off), 2 * md.h + __ldg(&sd0->layer[0][2].Np), et);
     }
@@ -604,14 +611,20 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
             }
             t2_epi_bar();
           }
-          for (int p = h0col; p < h1col; ++p) zrow[p] = xs[row * D + p];   // this thread's quarter of its own row (no div / mod)
+          if (INV) {   // z arrives in the flow's OUTPUT column order: logical column p lives at physical column sigma[p]
+            const int* sig = a.iblob + __ldg(&cdp->sigma_off);
+            for (int p = h0col; p < h1col; ++p) zrow[__ldg(sig + p)] = xs[row * D + p];
+          } else {
+            for (int p = h0col; p < h1col; ++p) zrow[p] = xs[row * D + p];   // this thread's quarter of its own row (no div / mod)
+          }
           if (g == 0) for (int p = D; p < Dv; ++p) zrow[p] = 0.f;         // scratch column(s): target of padded table entries
         }
         ptx::cp_async_wait_all();                    // (first component of the launch: the prologue's staging copies)
         t2_epi_bar();
         e_x += T2_CLOCK() - e_tmp;
         float lsum = 0.f;                            // this thread's share of the data-dependent log-det
-        for (int k = 0; k < md.K; ++k, ++stepc) {
+        for (int kk = 0; kk < md.K; ++kk, ++stepc) {
+          const int k = INV ? md.K - 1 - kk : kk;
           e_tmp = T2_CLOCK();
           if (tr) T2_TRACE(72 + 40 * (g & 1));
           if (PROF && tr && g == 0 && a.prof != nullptr && blockIdx.x == 0 && units == kT2TraceUnit + 1 && lane == 0) a.prof[32 + 201] = clock64();
@@ -621,10 +634,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           const float4* tab1 = tab_s + (stepc & 1u) * (2 * kEpPad);          // staged by the previous step
           const float4* tab2 = tab1 + kEpPad;
           // the step after this one (next k, next component, or the first step of this CTA's next tile)
-          const StepDesc* sd_next = (k + 1 < md.K) ? sd + 1
-                                    : (c + 1 < ce) ? a.steps + (c + 1) * md.K
+          const int kfirst = INV ? md.K - 1 : 0;
+          const StepDesc* sd_next = (kk + 1 < md.K) ? (INV ? sd - 1 : sd + 1)
+                                    : (c + 1 < ce) ? a.steps + (c + 1) * md.K + kfirst
                                     : (u + (int)gridDim.x < a.num_units)
-                                        ? a.steps + (a.c0 + ((u + (int)gridDim.x) % a.split) * a.comps_per_unit) * md.K
+                                        ? a.steps + (a.c0 + ((u + (int)gridDim.x) % a.split) * a.comps_per_unit) * md.K + kfirst
                                         : nullptr;
           // ---- ActNorm / eval-BatchNorm affine fused into the gather of z1 -> A0 (fp16, canonical layout, zero padded) ----
           {
@@ -638,10 +652,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               for (int e = 0; e < 8; ++e) t[e] = tab1[ch * 8 + e];
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = zrow[__float_as_int(t[e].w)];
+              if (INV) {   // the MLP input is z1 as it stands; the row keeps the un-normalised value (inverse tables)
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = (v[e] + t[e].x) * t[e].y + t[e].z;
+                for (int e = 0; e < 8; ++e) if (ch * 8 + e < in_dim) zrow[__float_as_int(t[e].w)] = (v[e] + t[e].x) * t[e].y + t[e].z;
+              } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) if (ch * 8 + e < in_dim) zrow[__float_as_int(t[e].w)] = v[e];   // never write the scratch column
+                for (int e = 0; e < 8; ++e) v[e] = (v[e] + t[e].x) * t[e].y + t[e].z;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (ch * 8 + e < in_dim) zrow[__float_as_int(t[e].w)] = v[e];   // never write the scratch column
+              }
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = (ch * 8 + e < in_dim) ? v[e] : 0.f;
               {   // a value that fp16 cannot hold (|v| > 65504, inf, NaN) would silently become inf / NaN in the GEMM operand
@@ -711,7 +730,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
               t2_stage_bias_async(bias_s + ((units + 1) & 1u) * bstride, a.fblob + mn[5], 2 * md.h + mn[3], et);
               if (et >= kT2EpiThreads - 2 * kEpPad) {
                 const int i = et - (kT2EpiThreads - 2 * kEpPad);
-                ptx::cp_async16(tab_s + ((stepc + 1) & 1u) * (2 * kEpPad) + i, reinterpret_cast<const float4*>(a.fblob + mn[7]) + i);
+                ptx::cp_async16(tab_s + ((stepc + 1) & 1u) * (2 * kEpPad) + i, reinterpret_cast<const float4*>(a.fblob + mn[7]) + (INV ? 2 * kEpPad : 0) + i);
               }
             }
             // ---- layer 2: chunk j in slot j & 1 -> act -> fp16 pairs packed in place = k-piece j of the last layer's A
@@ -786,9 +805,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                   const float shift = __uint_as_float(r[2 * jj]) + b.x;
                   const float raw = __uint_as_float(r[2 * jj + 1]) + b.y;
                   const float s = __fdividef(1.0f, 1.0f + __expf(-(raw + 2.0f)));      // sigmoid(raw + 2), glow.py:333
-                  const float zn = (z[jj] + t[jj].x) * t[jj].y + t[jj].z;
-                  z[jj] = (zn + shift) * s;                                             // glow.py:334-335
-                  lsum += (j < out_dim) ? __logf(s) : 0.f;                              // glow.py:338
+                  if (INV) {
+                    const float y = __fdividef(z[jj], s) - shift;                       // glow.py:354-356
+                    z[jj] = (y + t[jj].x) * t[jj].y + t[jj].z;                          // ActNorm reverse, layers.py:505-518
+                    lsum -= (j < out_dim) ? __logf(s) : 0.f;                            // glow.py:357
+                  } else {
+                    const float zn = (z[jj] + t[jj].x) * t[jj].y + t[jj].z;
+                    z[jj] = (zn + shift) * s;                                           // glow.py:334-335
+                    lsum += (j < out_dim) ? __logf(s) : 0.f;                            // glow.py:338
+                  }
                 }
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) if (g * 8 + jj < out_dim) zrow[__float_as_int(t[jj].w)] = z[jj];
@@ -805,15 +830,22 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
                   for (int jj = 0; jj < 8; ++jj) {
                     const int j = c0 + half * 8 + jj;
                     const float acc = __uint_as_float(r[half * 8 + jj]) + bias[j];
-                    const float zn = (z[jj] + t[jj].x) * t[jj].y + t[jj].z;
+                    const float zn = INV ? 0.f : (z[jj] + t[jj].x) * t[jj].y + t[jj].z;
                     if (MV != 2 && md.kind == GBNF_KIND_GLOW) {
-                      z[jj] = zn + acc;                                                 // additive coupling, glow.py:328-329
+                      if (INV) z[jj] = ((z[jj] - acc) + t[jj].x) * t[jj].y + t[jj].z;   // glow.py:350, then ActNorm reverse
+                      else     z[jj] = zn + acc;                                        // additive coupling, glow.py:328-329
                     } else if (net == 0) {                                              // RealNVP t_net: keep the shift
                       if (j < out_dim) sh[row * plan.out_max + j] = acc;
                     } else {                                                            // RealNVP s_net: transform
                       const float tt = (j < out_dim) ? sh[row * plan.out_max + j] : 0.f;
-                      z[jj] = tt + zn * __expf(acc);                                    // transformations.py:575
-                      lsum += (j < out_dim) ? acc : 0.f;                                // transformations.py:577
+                      if (INV) {
+                        const float y = (z[jj] - tt) * __expf(-acc);                    // inverse of transformations.py:575
+                        z[jj] = (y + t[jj].x) * t[jj].y + t[jj].z;                      // eval-BatchNorm inverse
+                        lsum -= (j < out_dim) ? acc : 0.f;
+                      } else {
+                        z[jj] = tt + zn * __expf(acc);                                  // transformations.py:575
+                        lsum += (j < out_dim) ? acc : 0.f;                              // transformations.py:577
+                      }
                     }
                   }
                   if ((MV != 2 && md.kind == GBNF_KIND_GLOW) || net == 1) {
@@ -845,7 +877,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
         t2_quad_bar(quad);
         if (g == 0) {
           q += part[row] + part[kTcRows + row] + part[2 * kTcRows + row];
-          const float ldj_tot = (lsum + part2[row] + part2[kTcRows + row] + part2[2 * kTcRows + row]) + ldj_const;
+          const float ldj_tot = (lsum + part2[row] + part2[kTcRows + row] + part2[2 * kTcRows + row]) + (INV ? -ldj_const : ldj_const);
           const float lq = (base_const - q) + ldj_tot;
           if (gr < a.B) {
             if (a.logq) a.logq[gr * a.ld_logq + (c - a.c0)] = lq;
@@ -854,8 +886,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           if (a.G_ll != nullptr && c < a.n_mix) __stcg(a.lse_terms + ((long long)tile * kTcRows + row) * a.n_mix + c, misc->coef[c] + lq);
         }
         if (a.z_out != nullptr && gr < a.B) {
-          const int* sig = a.iblob + __ldg(&cdp->sigma_off);
-          for (int j = h0col; j < h1col; ++j) a.z_out[gr * D + j] = zrow[__ldg(sig + j)];
+          if (INV) {   // physical == logical column order at the flow's input
+            for (int j = h0col; j < h1col; ++j) a.z_out[gr * D + j] = zrow[j];
+          } else {
+            const int* sig = a.iblob + __ldg(&cdp->sigma_off);
+            for (int j = h0col; j < h1col; ++j) a.z_out[gr * D + j] = zrow[__ldg(sig + j)];
+          }
         }
       }
       if (a.G_ll != nullptr) {
@@ -900,9 +936,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
 #undef T2_CLOCK
 #undef T2_TRACE
 
-template <int T, int P, int Q, int MV = 0>
+template <int T, int P, int Q, int MV = 0, int INV = 0>
 inline cudaError_t tc2_configure_one() {
-  return cudaFuncSetAttribute(coupling_tc2_kernel<T, P, Q, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return cudaFuncSetAttribute(coupling_tc2_kernel<T, P, Q, MV, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 // Instantiations.  Production (PROF = 0): geometry NQT in {4 (h = 512), 2 (h = 256), 0 (read from the model)} x model variant
 // MV in {0 generic, 1 Glow / affine / tanh, 2 RealNVP / tanh} x both tanh modes; profiling builds (PROF = 1, 2) only exist for the
@@ -917,7 +953,15 @@ inline cudaError_t tc2_configure() {
 #define T2_CFG_PROD(Q, MV) if (e == cudaSuccess) e = tc2_configure_one<0, 0, Q, MV>(); if (e == cudaSuccess) e = tc2_configure_one<1, 0, Q, MV>();
   T2_FOR_PROD(T2_CFG_PROD)
 #undef T2_CFG_PROD
+  if (e == cudaSuccess) e = tc2_configure_one<0, 0, 0, 0, 1>();      // inverse direction: generic geometry / model variant
+  if (e == cudaSuccess) e = tc2_configure_one<1, 0, 0, 0, 1>();
   return e;
+}
+
+inline int tc2_launch_inverse(const CouplingArgs& a, const TcPlan& p, int grid, cudaStream_t st) {
+  if (p.tanh_mode == 0) coupling_tc2_kernel<0, 0, 0, 0, 1><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
+  else                  coupling_tc2_kernel<1, 0, 0, 0, 1><<<grid, kT2Threads, p.smem_bytes, st>>>(a, p);
+  return 0;
 }
 
 inline int tc2_launch(const CouplingArgs& a, const TcPlan& p, int grid, cudaStream_t st, int prof) {

@@ -51,9 +51,9 @@ struct Tc3Misc {
   uint64_t sbr;       // epilogue -> MMA : slot B read out                                               (16 arrivals)
   uint64_t sr;        // epilogue -> MMA : A2 piece packed in slot A                                     (16 arrivals)
   uint64_t l3f;       // MMA -> epilogue : partial last-layer product complete                           (commit)
-  uint64_t xfull;     // PEER epilogue -> epilogue : both halves of a chunk's partial sums are in my exchange buffer (32 remote arrivals)
-  uint64_t x3full;    // PEER epilogue -> epilogue : the peer's partial last-layer product is in my exchange buffer (16 remote arrivals)
-  uint64_t xfree;     // PEER epilogue -> epilogue : the peer has consumed what I last wrote into ITS exchange buffer (16 remote arrivals)
+  uint64_t xfull;     // PEER epilogue -> epilogue : both halves of a chunk's partial sums are in my exchange buffer (armed by me with expect_tx; the peer's two bulk copies complete it)
+  uint64_t x3full;    // PEER epilogue -> epilogue : the peer's partial last-layer product is in my exchange buffer (armed by me; one bulk copy of the peer completes it)
+  uint64_t xfree;     // PEER epilogue -> epilogue : the peer has consumed what I last wrote into ITS exchange buffer (512 remote arrivals)
   uint32_t tmem_base;
   uint32_t last_flag;
   int meta[2][8];     // per step (double buffered): in_dim, out_dim, Kp of layer 1, Np of the last layer
@@ -79,7 +79,7 @@ inline bool tc3_make_plan(const ModelDims& md, const std::vector<StepDesc>& step
   p->off_zs = o;   o = al(o + kTcRows * md.Dv * 4);
   p->off_a0 = o;   o = al(o + (k0p / 16) * 4096);         // also the per-row partial sums at the end of a component (3 KB)
   p->off_a1 = o;   o = al(o + kT3XBytes);                 // here: the exchange buffer the PEER writes
-  p->off_sh = o;
+  p->off_sh = o;   o = al(o + kT3XBytes / 2);             // here: staging buffer of one shipped half chunk (source of the bulk copy)
   p->off_misc = o; o = al(o + kT3MiscBytes);
   p->off_bias = o; o = al(o + 2 * kT3BiasFloats * 4);
   p->off_tab = o;  o = al(o + 2 * 2 * kEpPad * 16);
@@ -139,7 +139,12 @@ __device__ __forceinline__ void t3_act_pack32_add(const uint32_t (&r)[32], const
   for (int q = 0; q < 16; ++q) p[q] = pack_half2(tc_act<ACT, TANH_MODE>(v[2 * q]), tc_act<ACT, TANH_MODE>(v[2 * q + 1]));
 }
 
-template <int TANH_MODE>
+// PROF = 1: per-role cycle counters of CTA 0 (rank 0 of pair 0) in a.prof (gbnf_get_profile): [0] MMA warp total, [1] wait ring,
+// [2] wait a0r + a1r, [3] wait slot B, [4] wait packed piece, [5] passes; [8] epilogue (thread 0) total, [9] wait l1f, [10] wait l2own,
+// [11] wait xfull, [12] wait l2ship, [13] wait xfree, [14] wait l3f, [15] wait x3full, [19] gather, [20] layer-1 epilogues,
+// [21] own epilogues, [22] ship epilogues, [23] transform + end-of-pass barrier; [16] producer total, [17] wait empty.
+#define T3_CLK() (PROF ? clock64() : 0LL)
+template <int TANH_MODE, int PROF = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupling_tc3_kernel(CouplingArgs a, TcPlan plan) {
   extern __shared__ __align__(1024) unsigned char smem[];
   asm volatile(".reg .pred t3_p_full;" ::);
@@ -148,6 +153,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
   float* zs = reinterpret_cast<float*>(smem + plan.off_zs);
   unsigned char* A0 = smem + plan.off_a0;
   float4* xb = reinterpret_cast<float4*>(smem + plan.off_a1);          // exchange buffer (written by the peer)
+  float4* stg = reinterpret_cast<float4*>(smem + plan.off_sh);         // what I ship next (read by my bulk copy)
   float* bias_s = reinterpret_cast<float*>(smem + plan.off_bias);
   float4* tab_s = reinterpret_cast<float4*>(smem + plan.off_tab);
   Tc3Misc* misc = reinterpret_cast<Tc3Misc*>(smem + plan.off_misc);
@@ -163,8 +169,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
     for (int i = 0; i < 4; ++i) { ptx::mbar_init(&misc->a1r[i], 16); ptx::mbar_init(&misc->l1f[i], 1); }
     ptx::mbar_init(&misc->l2own, 1); ptx::mbar_init(&misc->l2ship, 1);
     ptx::mbar_init(&misc->sbr, 16); ptx::mbar_init(&misc->sr, 16); ptx::mbar_init(&misc->l3f, 1);
-    ptx::mbar_init(&misc->xfull, 32); ptx::mbar_init(&misc->x3full, 16); ptx::mbar_init(&misc->xfree, 16);
+    ptx::mbar_init(&misc->xfull, 1); ptx::mbar_init(&misc->x3full, 1); ptx::mbar_init(&misc->xfree, kT3EpiThreads);
     ptx::fence_mbar_init();
+    ptx::mbar_arrive_expect_tx(&misc->xfull, kT3XBytes);     // armed for the first chunk the peer ships (two 32 KB bulk copies)
     if (a.G_ll != nullptr) mixture_coefficients(a.rho, a.n_mix, a.skip_c, a.mix_mode, misc->coef);
   }
   if (warp == 1) ptx::tmem_alloc(&misc->tmem_base, 512);
@@ -179,8 +186,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
     // ===================================== TMA producer =====================================================
     uint32_t par = 0;
     int slot = 0;
+    const long long p_t0 = T3_CLK();
+    long long p_wait = 0;
     auto push = [&](const __half* src, uint32_t bytes) {
+      const long long tw = T3_CLK();
       t2_wait(&misc->empty[slot], par ^ 1u, a.error_flag, 10, lane);
+      p_wait += T3_CLK() - tw;
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&misc->full[slot], bytes);
         ptx::tma_bulk_g2s(ring + (size_t)slot * kT3StageBytes, src, bytes, &misc->full[slot]);
@@ -212,12 +223,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           });
         }
     }
+    if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) { a.prof[16] = T3_CLK() - p_t0; a.prof[17] = p_wait; }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================================
     uint32_t units = 0;
     uint32_t n_sbr = 0, n_sr = 0;                    // waits done so far on the slot-B / packed-piece barriers
     int nslot = 0, slot = 0;
     uint32_t npar = 0;
+    const long long m_t0 = T3_CLK();
+    long long m_wf = 0, m_wa = 0, m_wb = 0, m_ws = 0, tw;
     const uint64_t a0_desc = ptx::make_smem_desc(ptx::smem_u32(A0));
     const uint64_t ring_desc = ptx::make_smem_desc(ptx::smem_u32(ring));
     const uint32_t idesc_128 = ptx::make_idesc_f16(128, 128);
@@ -232,7 +246,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
       slot = nslot;
       uint32_t full_ok;
       asm volatile("selp.u32 %0, 1, 0, t3_p_full;" : "=r"(full_ok));
+      tw = T3_CLK();
       if (!full_ok) ptx::mbar_wait(&misc->full[slot], npar, a.error_flag, 21);
+      m_wf += T3_CLK() - tw;
       ptx::tc_fence_after();
       if (++nslot == nst) { nslot = 0; npar ^= 1u; }
       test_full(&misc->full[nslot], npar);
@@ -256,9 +272,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           uint64_t l1_desc[2];
           int l1_slot[2];
           for (int j = 0; j < k0s; ++j) { l1_desc[j] = acquire(); l1_slot[j] = slot; }
+          tw = T3_CLK();
           wait_epi(&misc->a0r, upar, 20);
+          m_wa += T3_CLK() - tw;
           for (int q = 0; q < 4; ++q) {
+            tw = T3_CLK();
             if (q >= 2) wait_epi(&misc->a1r[q - 2], upar, 22);                    // its accumulator slot has been read out
+            m_wa += T3_CLK() - tw;
             if (ptx::elect_one()) {
               const uint32_t d = tbase + ((q & 1) ? kT3SlotB : kT3SlotA);
               // chunk q = k0s k-slabs of [128 x 16] at byte q * k0s * 4096 of the W1 half image (16 KB per held stage)
@@ -271,8 +291,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
             }
             __syncwarp();
           }
+          tw = T3_CLK();
           wait_epi(&misc->a1r[2], upar, 22);
           wait_epi(&misc->a1r[3], upar, 22);          // all of A1_p exists, slots A and B are free
+          m_wa += T3_CLK() - tw;
           // ---- layer 2 (partial sums over my K half) and my partial last-layer product ----
           t3_schedule(p, [&](int op, int x, int y) {
             if (op == T3_OP_OWN) {
@@ -290,7 +312,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
                 __syncwarp();
               }
             } else if (op == T3_OP_SHIP) {
+              tw = T3_CLK();
               wait_epi(&misc->sbr, (n_sbr & 1u) ^ 1u, 25);                        // slot B read out (passes the first time)
+              m_wb += T3_CLK() - tw;
               ++n_sbr;
               for (int t = 0; t < 4; ++t) {
                 const uint64_t bd = acquire();
@@ -309,7 +333,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
               // last-layer piece of own chunk number x: A2 packed in slot A [0, 64) x its k-slabs of W3 -> last-layer accumulator
               const uint64_t bd = acquire();
               const int cur = slot;
+              tw = T3_CLK();
               wait_epi(&misc->sr, n_sr & 1u, 23);
+              m_ws += T3_CLK() - tw;
               ++n_sr;
               if (ptx::elect_one()) {
                 const uint32_t at = tbase + kT3SlotA, d = tbase + kT3AccL3;
@@ -322,6 +348,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
             }
           });
         }
+    }
+    if (PROF && a.prof != nullptr && blockIdx.x == 0 && lane == 0) {
+      a.prof[0] = T3_CLK() - m_t0; a.prof[1] = m_wf; a.prof[2] = m_wa; a.prof[3] = m_wb; a.prof[4] = m_ws; a.prof[5] = units;
     }
   } else {
     // ===================================== epilogue / elementwise warps =====================================
@@ -336,6 +365,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
     const int h0col = min(D, g * dq), h1col = min(D, (g + 1) * dq);
     uint32_t units = 0;
     uint32_t n_own = 0, n_ship = 0, n_xfree = 0;     // waits done so far on l2own / xfull, l2ship, xfree
+    const long long e_t0 = T3_CLK();
+    long long e_l1f = 0, e_own = 0, e_xfull = 0, e_ship = 0, e_xfree = 0, e_l3f = 0, e_x3 = 0, e_g = 0, e_c1 = 0, e_c2 = 0, e_c3 = 0, e_c4 = 0, tq;
     float* const part = reinterpret_cast<float*>(A0);
     float* const part2 = part + 3 * kTcRows;
     const uint32_t peer = (uint32_t)(p ^ 1);
@@ -343,11 +374,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
     const uint32_t xfull_peer = ptx::mapa(ptx::smem_u32(&misc->xfull), peer);
     const uint32_t x3full_peer = ptx::mapa(ptx::smem_u32(&misc->x3full), peer);
     const uint32_t xfree_peer = ptx::mapa(ptx::smem_u32(&misc->xfree), peer);
-    auto remote_arrive = [&](uint32_t bar_cluster_addr) {
-      ptx::fence_acq_rel_cluster();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_remote(bar_cluster_addr);
-    };
+    // EVERY lane arrives (release at cluster scope orders that lane's own DSMEM stores / exchange-buffer loads before the
+    // arrival): a cluster-scope fence per lane followed by one elected arrival stalled every warp on MEMBAR for thousands of
+    // cycles per hand-off (ncu: 24 % of the warp samples)
+    auto remote_arrive = [&](uint32_t bar_cluster_addr) { ptx::mbar_arrive_remote(bar_cluster_addr); };
     // staging of one pass's constants: biases (b1 own half | b2 own chunks | b3), gather-order tables, scalars
     auto stage_pass = [&](const StepDesc* sd, int buf) {
       float* bdst = bias_s + buf * kT3BiasFloats;
@@ -415,6 +445,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
                                                                  : nullptr;
           const int act_kind = (md.act == GBNF_ACT_RELU) ? 2 : 1;
           // ---- ActNorm affine fused into the gather of z1 -> A0 (both CTAs build the same image) ----
+          tq = T3_CLK();
           {
             const int nch = meta[2] >> 3;
             for (int ch = g; ch < nch; ch += 4) {
@@ -442,9 +473,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           ptx::fence_proxy_async_smem();
           ptx::tc_fence_before();
           t2_warp_arrive(&misc->a0r, lane);
+          if (et == 0) ptx::mbar_arrive_expect_tx(&misc->x3full, (uint32_t)np3 * 512u);   // this pass's partial last-layer product of the peer
+          e_g += T3_CLK() - tq;
           // ---- layer 1: my 512 hidden units, chunk q -> bias + act -> fp16 pairs -> A1 quarter q ----
           for (int q = 0; q < 4; ++q) {
+            tq = T3_CLK();
             t2_wait(&misc->l1f[q], upar, a.error_flag, 30, lane);
+            e_l1f += T3_CLK() - tq;
+            tq = T3_CLK();
             ptx::tc_fence_after();
             uint32_t pk[16];
             {
@@ -458,6 +494,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             t2_warp_arrive(&misc->a1r[q], lane);
+            e_c1 += T3_CLK() - tq;
           }
           // the next pass's constants (other buffer: its last readers finished a pass ago)
           if (sd_next != nullptr) stage_pass(sd_next, buf ^ 1);
@@ -465,10 +502,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           t3_schedule(p, [&](int op, int x, int y) {
             if (op == T3_OP_OWN) {
               const int m = x >> 1;
+              tq = T3_CLK();
               t2_wait(&misc->l2own, n_own & 1u, a.error_flag, 31, lane);
+              e_own += T3_CLK() - tq;
               ptx::tc_fence_after();
+              tq = T3_CLK();
               ptx::mbar_wait_cluster(&misc->xfull, n_own & 1u, a.error_flag, 33);   // the peer's partial sums of this chunk have landed
               __syncwarp();
+              e_xfull += T3_CLK() - tq;
+              tq = T3_CLK();
               ++n_own;
               uint32_t pk[16];
               {
@@ -478,14 +520,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
                 if (act_kind == 1) t3_act_pack32_add<1, TANH_MODE>(r, xb + (g * 8) * kTcRows + row, bias_c + 512 + 128 * m + g * 32, pk, a.error_flag);
                 else               t3_act_pack32_add<2, TANH_MODE>(r, xb + (g * 8) * kTcRows + row, bias_c + 512 + 128 * m + g * 32, pk, a.error_flag);
               }
+              if (et == 0) ptx::mbar_arrive_expect_tx(&misc->xfull, kT3XBytes);   // arm the next chunk's phase (all waiters have
+                                                                                  // passed: the peer ships only after 512 xfree arrivals)
               remote_arrive(xfree_peer);             // my exchange buffer may be overwritten
               t2_quad_bar(quad);                     // all four threads of the row have read their columns of slot A
               ptx::tmem_st16(lane_base + kT3SlotA + (uint32_t)g * 16u, pk);
               ptx::tmem_st_wait();
               ptx::tc_fence_before();
               t2_warp_arrive(&misc->sr, lane);
+              e_c2 += T3_CLK() - tq;
             } else if (op == T3_OP_SHIP) {
+              tq = T3_CLK();
               t2_wait(&misc->l2ship, n_ship & 1u, a.error_flag, 34, lane);
+              e_ship += T3_CLK() - tq;
+              tq = T3_CLK();
               ++n_ship;
               ptx::tc_fence_after();
               uint32_t r[16];
@@ -493,21 +541,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
               ptx::tmem_ld_wait();
               ptx::tc_fence_before();
               t2_warp_arrive(&misc->sbr, lane);      // slot B may be overwritten by the next half
-              if (y == 0) {                          // the peer has consumed the previous chunk I wrote into its buffer
-                ptx::mbar_wait_cluster(&misc->xfree, (n_xfree & 1u) ^ 1u, a.error_flag, 35);
-                __syncwarp();
-                ++n_xfree;
-              }
-              const uint32_t dst = xb_peer + (uint32_t)(((16 * y + 4 * g) * kTcRows + row) * 16);
+              // The half chunk goes to the peer as ONE 32 KB bulk copy out of a local staging buffer (DSMEM stores from 512
+              // threads ran at ~10 B/clk and kept the epilogue warps busy for 3.4 k cycles per half; the copy engine moves
+              // ~20 B/clk on its own).  Staging layout = destination layout: float4 (c4 * 128 + row), c4 = column / 4.
+              if (et == 0) ptx::bulk_wait_read0();   // my previous copy has read the staging buffer
+              t2_epi_bar();
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                ptx::st_cluster_v4(dst + (uint32_t)(i * kTcRows * 16), __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-              remote_arrive(xfull_peer);
+                stg[(4 * g + i) * kTcRows + row] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+              ptx::fence_proxy_async_smem();
+              t2_epi_bar();
+              if (et == 0) {
+                if (y == 0) {                        // the peer has consumed the previous chunk I wrote into its buffer
+                  const long long tx = T3_CLK();
+                  ptx::mbar_wait_cluster(&misc->xfree, (n_xfree & 1u) ^ 1u, a.error_flag, 35);
+                  e_xfree += T3_CLK() - tx;
+                }
+                ptx::bulk_s2c(xb_peer + (uint32_t)y * (kT3XBytes / 2), stg, kT3XBytes / 2, xfull_peer);
+                ptx::bulk_commit();
+              }
+              if (y == 0) ++n_xfree;
+              e_c3 += T3_CLK() - tq;
             }
           });
           // ---- last layer: exchange the partial products, then the coupling transform on this thread's 16-column slice ----
+          tq = T3_CLK();
           t2_wait(&misc->l3f, upar, a.error_flag, 32, lane);
+          e_l3f += T3_CLK() - tq;
           ptx::tc_fence_after();
           const int c0 = g * 16;
           uint32_t r[16];
@@ -515,19 +576,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
             ptx::tmem_ld16(lane_base + kT3AccL3 + (uint32_t)c0, r);
             ptx::tmem_ld_wait();
           }
-          ptx::mbar_wait_cluster(&misc->xfree, (n_xfree & 1u) ^ 1u, a.error_flag, 36);
-          __syncwarp();
-          ++n_xfree;
+          if (et == 0) ptx::bulk_wait_read0();
+          t2_epi_bar();
           if (c0 < np3) {
-            const uint32_t dst = xb_peer + (uint32_t)(((4 * g) * kTcRows + row) * 16);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              ptx::st_cluster_v4(dst + (uint32_t)(i * kTcRows * 16), __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+              stg[(4 * g + i) * kTcRows + row] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                             __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
           }
-          remote_arrive(x3full_peer);
+          ptx::fence_proxy_async_smem();
+          t2_epi_bar();
+          if (et == 0) {
+            tq = T3_CLK();
+            ptx::mbar_wait_cluster(&misc->xfree, (n_xfree & 1u) ^ 1u, a.error_flag, 36);
+            e_xfree += T3_CLK() - tq;
+            ptx::bulk_s2c(xb_peer, stg, (uint32_t)np3 * 512u, x3full_peer);       // [np3 / 4][128 rows] float4
+            ptx::bulk_commit();
+          }
+          ++n_xfree;
+          tq = T3_CLK();
           ptx::mbar_wait_cluster(&misc->x3full, upar, a.error_flag, 37);
           __syncwarp();
+          e_x3 += T3_CLK() - tq;
+          tq = T3_CLK();
           if (c0 < np3) {
             float acc[16];
 #pragma unroll
@@ -583,6 +654,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           remote_arrive(xfree_peer);                 // I have read the peer's partial product out of my exchange buffer
           ptx::cp_async_wait_all();
           t2_epi_bar();                              // z2 updates, staged constants of the next pass
+          e_c4 += T3_CLK() - tq;
         }
         // ---- component log-density for this row (both CTAs hold the same z; rank 0 writes) ----
         float q = 0.f;
@@ -632,6 +704,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
         }
       }
     }
+    if (et == 0) ptx::bulk_wait0();                  // my last bulk copy into the peer has completed
+    if (PROF && a.prof != nullptr && blockIdx.x == 0 && et == 0) {
+      a.prof[8] = T3_CLK() - e_t0; a.prof[9] = e_l1f; a.prof[10] = e_own; a.prof[11] = e_xfull; a.prof[12] = e_ship; a.prof[13] = e_xfree;
+      a.prof[14] = e_l3f; a.prof[15] = e_x3; a.prof[19] = e_g; a.prof[20] = e_c1; a.prof[21] = e_c2; a.prof[22] = e_c3; a.prof[23] = e_c4;
+    }
     ptx::tc_fence_before();
   }
   __syncthreads();
@@ -643,14 +720,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
   }
 }
 
+#undef T3_CLK
 inline cudaError_t tc3_configure() {
   cudaError_t e = cudaFuncSetAttribute(coupling_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(coupling_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coupling_tc3_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return e;
+}
+
+// How many CTA pairs the device can keep resident at once (GPCs with an odd number of usable SMs strand one SM each): a
+// persistent grid larger than this would run its last clusters as a second wave.
+inline int tc3_max_pairs(const TcPlan& p, int num_sms) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * (num_sms / 2)), 1, 1);
+  cfg.blockDim = dim3(kT3Threads, 1, 1);
+  cfg.dynamicSmemBytes = p.smem_bytes;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, coupling_tc3_kernel<0>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / 2; }
+  return std::min(n, num_sms / 2);
 }
 
 // grid = 2 x (CTA pairs): the cluster dimension is a compile-time attribute of the kernel
-inline int tc3_launch(const CouplingArgs& a, const TcPlan& p, int pairs, cudaStream_t st) {
+inline int tc3_launch(const CouplingArgs& a, const TcPlan& p, int pairs, cudaStream_t st, int prof = 0) {
+  if (prof) { coupling_tc3_kernel<0, 1><<<2 * pairs, kT3Threads, p.smem_bytes, st>>>(a, p); return 0; }
   if (p.tanh_mode == 0) coupling_tc3_kernel<0><<<2 * pairs, kT3Threads, p.smem_bytes, st>>>(a, p);
   else                  coupling_tc3_kernel<1><<<2 * pairs, kT3Threads, p.smem_bytes, st>>>(a, p);
   return 0;

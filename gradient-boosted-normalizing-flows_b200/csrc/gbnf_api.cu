@@ -90,6 +90,7 @@ struct gbnf_ctx {
   TcPlan tc{};
   bool tc2 = false;              // pipelined tensor-core kernel (coupling_tc2.cuh) selected
   bool tc3 = false;              // CTA-pair tensor-core kernel for h = 1024 (coupling_tc3.cuh) selected
+  int tc3_pairs = 0;             // CTA pairs the device keeps resident at once (cudaOccupancyMaxActiveClusters)
   int profiling = 0;             // GBNF_PROF=1: cycle counters + event trace, 2: event trace only (gbnf_get_profile / _trace)
   int last_grid = 0;
   long long launches = 0;
@@ -170,7 +171,7 @@ int plan_layout(gbnf_ctx* h) {
       sd.vec_off = f; f += round_up_ll(3LL * md.Dv, 4);
       sd.idx_off = i; i += round_up_ll(sd.in_dim + sd.out_dim, 4);
       f = round_up_ll(f, 4);
-      sd.ep_off = f; f += 8LL * kEpPad;
+      sd.ep_off = f; f += 16LL * kEpPad;
       sd.eidx_off = 0;
       h->out_max = std::max(h->out_max, sd.out_dim);
       int n_last = sd.out_dim;
@@ -285,7 +286,7 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
   const int R = h->rows_per_cta;
   a.num_tiles = (int)((B + R - 1) / R);
   a.split = 1; a.comps_per_unit = c1 - c0; a.num_units = a.num_tiles;
-  const int workers = h->tc3 ? h->num_sms / 2 : h->num_sms;      // CTAs, or CTA pairs, that run concurrently
+  const int workers = h->tc3 ? h->tc3_pairs : h->num_sms;        // CTAs, or CTA pairs, that run concurrently
   if (h->cfg.gemm_mode != GBNF_GEMM_FP32 && (h->tc2 || h->tc3)) {
     // split every tile's components over S units when that shortens the critical CTA (waves x components per unit)
     const int ncomp = c1 - c0;
@@ -323,7 +324,7 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
     else if (R == 32) coupling_fp32_kernel<32><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
     else coupling_fp32_kernel<16><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
   } else {
-    int rc = h->tc3 ? tc3_launch(a, h->tc, grid, st) : h->tc2 ? tc2_launch(a, h->tc, grid, st, h->profiling) : tc_launch(a, h->tc, grid, st);
+    int rc = h->tc3 ? tc3_launch(a, h->tc, grid, st, h->profiling) : h->tc2 ? tc2_launch(a, h->tc, grid, st, h->profiling) : tc_launch(a, h->tc, grid, st);
     if (rc != 0) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: launch configuration rejected");
   }
   h->launches++;
@@ -400,10 +401,14 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
     CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_inverse_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_inverse_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CREATE_TRY(cudaFuncSetAttribute(coupling_fp32_inverse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   } else {
     CREATE_TRY(tc_configure(h->tc));
     CREATE_TRY(tc2_configure());
     CREATE_TRY(tc3_configure());
+    if (h->tc3) h->tc3_pairs = tc3_max_pairs(h->tc, h->num_sms);
   }
 #undef CREATE_TRY
   *out = h;
@@ -509,6 +514,44 @@ int gbnf_component_logq(gbnf_handle h, const float* d_x, int64_t B, int32_t c0, 
   ENTER(h);
   return launch_coupling(h, d_x, B, c0, c1, d_logq, c1 - c0, d_z_opt, d_ldj_opt, nullptr, 0, -1, 0, nullptr,
                          (cudaStream_t)stream);
+}
+
+int gbnf_component_inverse(gbnf_handle h, const float* d_z, int64_t B, int32_t c, float* d_x, float* d_ldj_opt, void* stream) {
+  if (!h) return fail(GBNF_ERR_INVALID, "null handle");
+  if (B < 0 || c < 0 || c >= h->cfg.C) return fail(GBNF_ERR_INVALID, "bad B or component index");
+  if (B == 0) return GBNF_OK;
+  if (!d_z || !d_x) return fail(GBNF_ERR_INVALID, "null pointer");
+  if (!h->packed[c]) return fail(GBNF_ERR_STATE, "component " + std::to_string(c) + " has not been packed");
+  const bool f16 = h->cfg.gemm_mode != GBNF_GEMM_FP32;
+  if (f16 && !h->tc2)
+    return fail(GBNF_ERR_INVALID, "inverse direction: the f16 tensor-core modes serve it through the pipelined kernel only (hidden width a "
+                                  "multiple of 128 up to 512, depth 1); use GBNF_GEMM_FP32 for this configuration");
+  ENTER(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  constexpr long long kMaxRowsPerLaunch = 1LL << 22;
+  for (long long r0 = 0; r0 < B; r0 += kMaxRowsPerLaunch) {
+    const long long nb = std::min(kMaxRowsPerLaunch, (long long)B - r0);
+    CouplingArgs a{};
+    a.x = d_z + r0 * h->md.D; a.B = nb; a.c0 = c; a.c1 = c + 1; a.z_out = d_x + r0 * h->md.D; a.ldj_out = d_ldj_opt ? d_ldj_opt + r0 : nullptr;
+    a.n_mix = 0; a.skip_c = -1;
+    a.steps = h->steps_d; a.comps = h->comps_d; a.fblob = h->fblob; a.iblob = h->iblob; a.wblob = h->wblob; a.md = h->md;
+    a.cc_off = h->cc_off; a.error_flag = h->flags; a.prof = nullptr;
+    const int R = h->rows_per_cta;
+    a.num_tiles = (int)((nb + R - 1) / R);
+    a.split = 1; a.comps_per_unit = 1; a.num_units = a.num_tiles;
+    const int grid = std::min(a.num_tiles, h->num_sms);
+    h->last_grid = grid;
+    if (!f16) {
+      if (R == 64) coupling_fp32_inverse_kernel<64><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
+      else if (R == 32) coupling_fp32_inverse_kernel<32><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
+      else coupling_fp32_inverse_kernel<16><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
+    } else {
+      tc2_launch_inverse(a, h->tc, grid, st);
+    }
+    h->launches++;
+    CUDA_TRY_H(h, cudaGetLastError());
+  }
+  return GBNF_OK;
 }
 
 int gbnf_mixture_logdensity(gbnf_handle h, const float* d_logq, int64_t B, int32_t ld, int32_t n_comp,

@@ -80,11 +80,15 @@ __global__ void pack_meta_kernel(PackMetaArgs a) {
     const int* idx2 = idx1 + sd.in_dim;
     float4* t1 = reinterpret_cast<float4*>(a.fblob + sd.ep_off);     // {add, mul, off, column (int bits)} in z1 order
     float4* t2 = t1 + kEpPad;                                         // same in z2 order
+    float4* u1 = t2 + kEpPad;                                         // INVERSE affine in the same form: x = (y + -off) * (1 / mul) + -add
+    float4* u2 = u1 + kEpPad;
     for (int j = 0; j < kEpPad; ++j) {
       const bool v1 = j < sd.in_dim, v2 = j < sd.out_dim;
       const int c1 = v1 ? idx1[j] : D, c2 = v2 ? idx2[j] : D;
       t1[j] = make_float4(v1 ? add[c1] : 0.f, v1 ? mul[c1] : 0.f, v1 ? off[c1] : 0.f, __int_as_float(c1));
       t2[j] = make_float4(v2 ? add[c2] : 0.f, v2 ? mul[c2] : 0.f, v2 ? off[c2] : 0.f, __int_as_float(c2));
+      u1[j] = make_float4(v1 ? -off[c1] : 0.f, v1 ? 1.0f / mul[c1] : 0.f, v1 ? -add[c1] : 0.f, __int_as_float(c1));
+      u2[j] = make_float4(v2 ? -off[c2] : 0.f, v2 ? 1.0f / mul[c2] : 0.f, v2 ? -add[c2] : 0.f, __int_as_float(c2));
     }
   }
   int* sig_out = a.iblob + a.cdesc.sigma_off;

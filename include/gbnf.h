@@ -130,6 +130,15 @@ int gbnf_set_base(gbnf_handle h, const float* d_mean, const float* d_scale, void
 int gbnf_component_logq(gbnf_handle h, const float* d_x, int64_t B, int32_t c0, int32_t c1, float* d_logq,
                         float* d_z_opt, float* d_ldj_opt, void* stream);
 
+/* Inverse direction (sampling): x = f_c^{-1}(z) for ONE component -- the exact inverse of gbnf_component_logq's flow, walked
+ * from the last coupling step to the first (coupling^-1, permutation^-1, ActNorm^-1 / eval-BatchNorm^-1).  Replaces
+ * `model(z=z, components=c, reverse=True)`: models/boosted_flow.py:209-218, models/glow.py:112-123,344-366,
+ * models/realnvp.py:97-113 (upstream's RealNVP decode pairs the wrong halves and its 1-D affine Glow decode raises; this is
+ * the mathematical inverse, pinned by decode(encode(x)) == x and by the reference's additive-Glow decode).
+ * d_z [B, D] in the flow's output column order, d_x [B, D]; d_ldj_opt [B] (may be NULL) receives the log-det of the
+ * inverse map (= -log_det_j of the forward map at x). */
+int gbnf_component_inverse(gbnf_handle h, const float* d_z, int64_t B, int32_t c, float* d_x, float* d_ldj_opt, void* stream);
+
 /* Mixture log-density from materialised per-component log q (d_logq is [B, ld], first n_comp columns used):
  * the 2-term logsumexp recursion of density_experiment.py:612-622 / :561-571 evaluated in its flat form
  * G = logsumexp_c(coef_c + logq_c).  d_rho is the RAW rho buffer [>= n_comp] (device);

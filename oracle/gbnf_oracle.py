@@ -124,6 +124,77 @@ def component_forward(model, x, c):
 
 
 # --------------------------------------------------------------------------------------
+# inverse direction (sampling): x = f_c^{-1}(z).  Upstream: Glow.decode glow.py:112-123 -> FlowNet.decode :254-260 ->
+# FlowStep.decode :344-366 (its affine branch sums over dim=[1,2,3] and raises on 1-D data; the additive branch runs and
+# is pinned by a golden fixture); RealNVPFlow.decode realnvp.py:97-113 / transformations.py:581-599 pairs the wrong halves
+#  and is NOT an inverse of encode.  The functions below are the exact mathematical inverses of the forward
+# steps above, in the reference's own order of operations (coupling^-1, permutation^-1, ActNorm^-1 / BatchNorm^-1).
+# --------------------------------------------------------------------------------------
+def glow_step_inverse(y, ldj, step, coupling="affine", act="tanh"):
+    D = y.shape[1]
+    h0 = D // 2
+    z1, z2 = y[:, :h0], y[:, h0:]
+    hh = mlp(z1, step["net"], act)
+    if coupling == "additive":
+        z2 = z2 - hh                                              # glow.py:350
+    else:
+        shift, raw = hh[:, 0::2], hh[:, 1::2]
+        scale = 1.0 / (1.0 + np.exp(-(raw + 2.0)))
+        z2 = z2 / scale - shift                                   # glow.py:354-356
+        ldj = ldj - np.sum(np.log(scale), axis=1)                 # glow.py:357
+    z = np.concatenate([z1, z2], axis=1)
+    zin = np.empty_like(z)
+    zin[:, step["perm"]] = z                                      # inverse of y = z[:, indices], layers.py:661-668
+    x = zin * np.exp(-step["an_logs"]) - step["an_bias"]          # ActNorm reverse: scale then center, layers.py:505-518
+    return x, ldj - np.sum(step["an_logs"])
+
+
+def realnvp_step_inverse(z, ldj, step, flipped, act="tanh"):
+    D = z.shape[1]
+    h0 = D // 2
+    n1 = D - h0 if flipped else h0                                # forward output is [z1, z2'] for both flips
+    z1, z2 = z[:, :n1], z[:, n1:]
+    t_act = "relu" if act == "mixed" else act
+    s_act = "tanh" if act == "mixed" else act
+    shift = mlp(z1, step["t"], t_act)
+    scale = mlp(z1, step["s"], s_act)
+    z2 = (z2 - shift) * np.exp(-scale)
+    x = np.concatenate([z2, z1], axis=1) if flipped else np.concatenate([z1, z2], axis=1)
+    ldj = ldj - np.sum(scale, axis=1)
+    bn = step.get("bn")
+    if bn is not None:                                            # inverse of batchnorm_eval
+        x_hat = (x - bn["beta"]) * np.exp(-bn["log_gamma"])
+        x = x_hat * np.sqrt(bn["var"] + x.dtype.type(BN_EPS)) + bn["mean"]
+        ldj = ldj - np.sum(bn["log_gamma"] - 0.5 * np.log(bn["var"] + x.dtype.type(BN_EPS)))
+    return x, ldj
+
+
+def component_inverse(model, z, c):
+    """x = f_c^{-1}(z) and the log-det of the INVERSE map (= -log_det_j of the forward map at x)."""
+    comp = model["components"][c]
+    x = z
+    ldj = np.zeros(z.shape[0], dtype=z.dtype)
+    for k in range(len(comp["steps"]) - 1, -1, -1):
+        step = comp["steps"][k]
+        if model["kind"] == "glow":
+            x, ldj = glow_step_inverse(x, ldj, step, model.get("coupling", "affine"), model.get("act", "tanh"))
+        else:
+            flipped = ((k + comp["flip_init"]) % 2) > 0
+            x, ldj = realnvp_step_inverse(x, ldj, step, flipped, model.get("act", "tanh"))
+    return x, ldj
+
+
+def assign_components(rho, n, u, exclude=-1):
+    """Per-sample component ids for mixture sampling under the inverse-CDF rule of sample_component:
+    j_i = #{k : cum_k < u_i}, cum = cumsum_fp64(rho[:n]) / sum."""
+    p = np.asarray(rho[:n], dtype=np.float64).copy()
+    if exclude >= 0:
+        p[exclude] = 0.0
+    cum = np.cumsum(p) / np.sum(p)
+    return np.minimum(np.searchsorted(cum, np.asarray(u, dtype=np.float64), side="left"), n - 1).astype(np.int64)
+
+
+# --------------------------------------------------------------------------------------
 # A.4  base densities
 # --------------------------------------------------------------------------------------
 def log_normal_standard(z):

@@ -129,6 +129,14 @@ def build_case(name):
         else:
             out["state0." + k] = v.numpy()
     out["seed"] = np.array(seed)
+    # inverse direction: the reference's own decode where it is not broken upstream (1-D Glow with ADDITIVE coupling:
+    # FlowStep.decode glow.py:344-366; the affine branch raises on 2-D tensors, RealNVP's decode is not an inverse -- SURVEY 7)
+    if args.component_type == "glow" and args.flow_coupling == "additive":
+        with torch.no_grad():
+            for c in range(model.num_components):
+                xr = model.flows[c](z=z32[c], y_onehot=None, temperature=None, reverse=True)
+                out[f"dec32.c{c}"] = xr.numpy()
+                out[f"dec64.c{c}"] = m64.flows[c](z=z64[c], y_onehot=None, temperature=None, reverse=True).numpy()
     md = extract_model(model, toy_base=toy_base)
     for k, v in orc.flatten_model(md).items():
         out["model." + k] = v

@@ -146,3 +146,30 @@ def test_torch_timing_variant_matches_numpy_oracle(golden):
         Gn = orc.mixture_recursion(g["logq32"], md["rho"], md["C"])
         np.testing.assert_allclose(G.numpy(), Gn, rtol=5e-6, atol=5e-6)
         np.testing.assert_allclose(w.numpy(), orc.boost_weights(Gn), rtol=2e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_inverse_round_trip_and_reference_decode(golden, name):
+    """The oracle's inverse direction: exact inverse of the reference's forward (fp64), and equal to the reference's own decode
+    where upstream's decode runs (1-D Glow, additive coupling: FlowStep.decode models/glow.py:344-366)."""
+    g = golden(name); md = golden_model(g)
+    m64 = orc.cast_model(md, np.float64)
+    for c in range(md["C"]):
+        x, ldj = orc.component_inverse(m64, g["z64"][c], c)
+        np.testing.assert_allclose(x, g["x"].astype(np.float64), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(ldj, -g["ldj64"][c], rtol=1e-6, atol=1e-6)
+        if f"dec64.c{c}" in g:
+            np.testing.assert_allclose(x, g[f"dec64.c{c}"], rtol=1e-12, atol=1e-12)
+            x32, _ = orc.component_inverse(md, g["z32"][c], c)
+            np.testing.assert_allclose(x32, g[f"dec32.c{c}"], rtol=2e-5, atol=2e-5)
+    assert any(k.startswith("dec64.") for k in golden("glow_d6_additive_relu"))
+
+
+def test_oracle_component_assignment_matches_sample_component():
+    rng = np.random.default_rng(3)
+    rho = rng.random(7).astype(np.float32) + 0.05
+    u = rng.random(500)
+    got = orc.assign_components(rho, 7, u)
+    assert all(got[i] == orc.sample_component(rho, 7, float(u[i])) for i in range(500))
+    got = orc.assign_components(rho, 7, u, exclude=3)
+    assert 3 not in got and all(got[i] == orc.sample_component(rho, 7, float(u[i]), exclude=3) for i in range(500))
