@@ -20,8 +20,8 @@
 //   slot B [384, 448): shipped half chunk (64 columns) | last-layer accumulator [448, 512).  Layer-1 accumulators use slots
 //   A / (B + last) before layer 2 starts.
 //   weights: one linear stream per (step, CTA) in the order the MMA warp consumes it, cut into 16 KB ring stages
-//   (pack_weight_tc3_kernel): W1 half | for J = 0..7: own chunk [32 k-slabs][128 x 16] or two shipped halves
-//   [32 k-slabs][64 x 16] | with the last-layer piece of an own chunk ([8 k-slabs][Np3 x 16]) following the op after it.
+//   (pack_weight_tc3_kernel): W1 half | for chunk pair m = 0..3: two shipped halves [32 k-slabs][64 x 16] of chunk
+//   2 m + 1 - p, then the own chunk 2 m + p [32 k-slabs][128 x 16] | last-layer pieces [8 k-slabs][Np3 x 16] per own chunk.
 //
 // Warp roles as in coupling_tc2.cuh: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..17 = epilogue (four threads per row).
 #pragma once
@@ -53,7 +53,7 @@ struct Tc3Misc {
   uint64_t l3f;       // MMA -> epilogue : partial last-layer product complete                           (commit)
   uint64_t xfull;     // PEER epilogue -> epilogue : both halves of a chunk's partial sums are in my exchange buffer (armed by me with expect_tx; the peer's two bulk copies complete it)
   uint64_t x3full;    // PEER epilogue -> epilogue : the peer's partial last-layer product is in my exchange buffer (armed by me; one bulk copy of the peer completes it)
-  uint64_t xfree;     // PEER epilogue -> epilogue : the peer has consumed what I last wrote into ITS exchange buffer (512 remote arrivals)
+  uint64_t xfree;     // PEER epilogue -> epilogue : the peer has consumed what I last wrote into ITS exchange buffer (16 remote arrivals, relaxed)
   uint32_t tmem_base;
   uint32_t last_flag;
   int meta[2][8];     // per step (double buffered): in_dim, out_dim, Kp of layer 1, Np of the last layer
@@ -77,9 +77,11 @@ inline bool tc3_make_plan(const ModelDims& md, const std::vector<StepDesc>& step
   p->K0p = k0p; p->out_max = out_max;
   uint32_t o = 0;
   p->off_zs = o;   o = al(o + kTcRows * md.Dv * 4);
-  p->off_a0 = o;   o = al(o + (k0p / 16) * 4096);         // also the per-row partial sums at the end of a component (3 KB)
   p->off_a1 = o;   o = al(o + kT3XBytes);                 // here: the exchange buffer the PEER writes
-  p->off_sh = o;   o = al(o + kT3XBytes / 2);             // here: staging buffer of one shipped half chunk (source of the bulk copy)
+  p->off_sh = o;                                          // here: staging buffer of one shipped half chunk (source of the bulk copy)
+  p->off_a0 = o;   o = al(o + kT3XBytes / 2);             // A0 (<= 8 KB, live from the gather to the last layer-1 MMA) and the per-row
+                                                          // partial sums at the end of a component ALIAS the staging buffer (live during
+                                                          // layer 2 and the exchange of the partial last-layer products)
   p->off_misc = o; o = al(o + kT3MiscBytes);
   p->off_bias = o; o = al(o + 2 * kT3BiasFloats * 4);
   p->off_tab = o;  o = al(o + 2 * 2 * kEpPad * 16);
@@ -98,21 +100,20 @@ inline bool tc3_make_plan(const ModelDims& md, const std::vector<StepDesc>& step
 //   L3   (m)      : last-layer piece of own chunk number m (J = 2 m + p), issued one op group later so that the epilogue has
 //                   had time to pack it; 1 ring stage
 enum { T3_OP_OWN = 0, T3_OP_SHIP, T3_OP_L3 };
+// SHIP FIRST: in chunk pair m both CTAs first produce what the PEER is waiting for (the shipped chunk 2 m + 1 - p), then their
+// own chunk 2 m + p, whose epilogue (peer's partial sums + tanh + pack) runs while the MMA warp is already busy with the next
+// pair's shipped halves; the own chunk's last-layer piece follows those.  (Own-first order chained the two CTAs: own(J) waited
+// for the peer's ship(J), which the peer only started after ITS own(J - 1), ... -- 8 serial hops per pass, measured 99 k cycles.)
 template <class F>
 __device__ __forceinline__ void t3_schedule(int p, F&& f) {
-  int pending = -1;                                   // own chunk whose last-layer piece has not been issued yet
 #pragma unroll
-  for (int J = 0; J < 8; ++J) {
-    if ((J & 1) == p) {
-      f(T3_OP_OWN, J, 0);
-      pending = J >> 1;
-      if (J == 7) { f(T3_OP_L3, pending, 0); pending = -1; }
-    } else {
-      f(T3_OP_SHIP, J, 0);
-      f(T3_OP_SHIP, J, 1);
-      if (pending >= 0) { f(T3_OP_L3, pending, 0); pending = -1; }
-    }
+  for (int m = 0; m < 4; ++m) {
+    f(T3_OP_SHIP, 2 * m + 1 - p, 0);
+    f(T3_OP_SHIP, 2 * m + 1 - p, 1);
+    if (m > 0) f(T3_OP_L3, m - 1, 0);
+    f(T3_OP_OWN, 2 * m + p, 0);
   }
+  f(T3_OP_L3, 3, 0);
 }
 
 template <int ACT, int TANH_MODE>
@@ -169,7 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
     for (int i = 0; i < 4; ++i) { ptx::mbar_init(&misc->a1r[i], 16); ptx::mbar_init(&misc->l1f[i], 1); }
     ptx::mbar_init(&misc->l2own, 1); ptx::mbar_init(&misc->l2ship, 1);
     ptx::mbar_init(&misc->sbr, 16); ptx::mbar_init(&misc->sr, 16); ptx::mbar_init(&misc->l3f, 1);
-    ptx::mbar_init(&misc->xfull, 1); ptx::mbar_init(&misc->x3full, 1); ptx::mbar_init(&misc->xfree, kT3EpiThreads);
+    ptx::mbar_init(&misc->xfull, 1); ptx::mbar_init(&misc->x3full, 1); ptx::mbar_init(&misc->xfree, 16);
     ptx::fence_mbar_init();
     ptx::mbar_arrive_expect_tx(&misc->xfull, kT3XBytes);     // armed for the first chunk the peer ships (two 32 KB bulk copies)
     if (a.G_ll != nullptr) mixture_coefficients(a.rho, a.n_mix, a.skip_c, a.mix_mode, misc->coef);
@@ -209,14 +210,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           const __half* w1 = wb + __ldg(&sd->layer[0][0].w_off) + (size_t)p * kT3HH * kp0;
           const __half* w2 = wb + __ldg(&sd->layer[0][1].w_off) + (size_t)p * kT3H * kT3HH;
           const __half* w3 = wb + __ldg(&sd->layer[0][2].w_off) + (size_t)p * np3 * kT3HH;
+          // The packed weights of this configuration (184 MB at cfg5) do not fit in L2 and every CTA pair reaches a step at about
+          // the same time, so without help each ring stage's first touch is an HBM miss that ALL pairs wait for: pull the stream
+          // into L2 well ahead of the ring (256 KB within the step, the head of the next step at the start of this one).
+          constexpr uint32_t kAhead = 262144;
+          if (ptx::elect_one()) {
+            const StepDesc* sn = (k + 1 < md.K) ? sd + 1 : (c + 1 < ce) ? a.steps + (c + 1) * md.K : nullptr;
+            if (sn != nullptr) {
+              const int kpn = __ldg(&sn->layer[0][0].Kp), npn = __ldg(&sn->layer[0][2].Np);
+              ptx::prefetch_l2(wb + __ldg(&sn->layer[0][0].w_off) + (size_t)p * kT3HH * kpn, (uint32_t)(kT3HH * kpn * 2));
+              ptx::prefetch_l2(wb + __ldg(&sn->layer[0][1].w_off) + (size_t)p * kT3H * kT3HH, kAhead);
+              ptx::prefetch_l2(wb + __ldg(&sn->layer[0][2].w_off) + (size_t)p * npn * kT3HH, (uint32_t)(npn * kT3HH * 2));
+            }
+          }
+          __syncwarp();
+          uint32_t w2_pos = 0;                                  // bytes of my W2 stream pushed so far
+          auto push_w2 = [&](const __half* src) {
+            if (w2_pos + kAhead < (uint32_t)(kT3H * kT3HH * 2) && ptx::elect_one())
+              ptx::prefetch_l2(reinterpret_cast<const unsigned char*>(w2) + w2_pos + kAhead, kT3StageBytes);
+            w2_pos += kT3StageBytes;
+            push(src, kT3StageBytes);
+          };
           for (int j = 0; j < (kp0 >> 4); ++j) push(w1 + (size_t)j * 8192, kT3StageBytes);     // W1 half: (Kp0 / 16) x 16 KB
           t3_schedule(p, [&](int op, int x, int y) {
             if (op == T3_OP_OWN) {
-              const __half* base = w2 + (size_t)x * 65536;
-              for (int t = 0; t < 8; ++t) push(base + (size_t)t * 8192, kT3StageBytes);
+              const __half* base = w2 + (size_t)(2 * (x >> 1) + 1) * 65536;       // pair m = x >> 1: [shipped block][own block]
+              for (int t = 0; t < 8; ++t) push_w2(base + (size_t)t * 8192);
             } else if (op == T3_OP_SHIP) {
-              const __half* base = w2 + (size_t)x * 65536 + (size_t)y * 32768;
-              for (int t = 0; t < 4; ++t) push(base + (size_t)t * 8192, kT3StageBytes);
+              const __half* base = w2 + (size_t)(2 * (x >> 1)) * 65536 + (size_t)y * 32768;
+              for (int t = 0; t < 4; ++t) push_w2(base + (size_t)t * 8192);
             } else {
               push(w3 + (size_t)x * 8 * np3 * 16, (uint32_t)(8 * np3) * 32u);
             }
@@ -377,7 +399,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
     // EVERY lane arrives (release at cluster scope orders that lane's own DSMEM stores / exchange-buffer loads before the
     // arrival): a cluster-scope fence per lane followed by one elected arrival stalled every warp on MEMBAR for thousands of
     // cycles per hand-off (ncu: 24 % of the warp samples)
-    auto remote_arrive = [&](uint32_t bar_cluster_addr) { ptx::mbar_arrive_remote(bar_cluster_addr); };
+    // xfree only says "my loads from the exchange buffer are done": no writes to publish, so one RELAXED arrival per warp, issued
+    // after the arithmetic that consumed the loaded values (a release arrival per lane cost ~1 k cycles per hand-off)
+    auto remote_arrive = [&](uint32_t bar_cluster_addr) {
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_remote_relaxed(bar_cluster_addr);
+    };
     // staging of one pass's constants: biases (b1 own half | b2 own chunks | b3), gather-order tables, scalars
     auto stage_pass = [&](const StepDesc* sd, int buf) {
       float* bdst = bias_s + buf * kT3BiasFloats;
@@ -520,14 +547,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
                 if (act_kind == 1) t3_act_pack32_add<1, TANH_MODE>(r, xb + (g * 8) * kTcRows + row, bias_c + 512 + 128 * m + g * 32, pk, a.error_flag);
                 else               t3_act_pack32_add<2, TANH_MODE>(r, xb + (g * 8) * kTcRows + row, bias_c + 512 + 128 * m + g * 32, pk, a.error_flag);
               }
-              if (et == 0) ptx::mbar_arrive_expect_tx(&misc->xfull, kT3XBytes);   // arm the next chunk's phase (all waiters have
-                                                                                  // passed: the peer ships only after 512 xfree arrivals)
-              remote_arrive(xfree_peer);             // my exchange buffer may be overwritten
               t2_quad_bar(quad);                     // all four threads of the row have read their columns of slot A
               ptx::tmem_st16(lane_base + kT3SlotA + (uint32_t)g * 16u, pk);
               ptx::tmem_st_wait();
               ptx::tc_fence_before();
               t2_warp_arrive(&misc->sr, lane);
+              if (et == 0) ptx::mbar_arrive_expect_tx(&misc->xfull, kT3XBytes);   // arm the next chunk's phase (all waiters have
+                                                                                  // passed: the peer ships only after 16 xfree arrivals)
+              remote_arrive(xfree_peer);             // my exchange buffer may be overwritten
               e_c2 += T3_CLK() - tq;
             } else if (op == T3_OP_SHIP) {
               tq = T3_CLK();
@@ -653,6 +680,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           }
           remote_arrive(xfree_peer);                 // I have read the peer's partial product out of my exchange buffer
           ptx::cp_async_wait_all();
+          if (et == 0) ptx::bulk_wait_read0();       // my copy has read the staging buffer, which the next gather (A0) overwrites
           t2_epi_bar();                              // z2 updates, staged constants of the next pass
           e_c4 += T3_CLK() - tq;
         }
@@ -769,7 +797,9 @@ __global__ void pack_weight_tc3_kernel(const float* __restrict__ W, const float*
       n = kT3HH * p + 128 * q + (rr / 128) * 8 + (rr % 64) / 8;
       k = 16 * slab + ((rr % 128) / 64) * 8 + rr % 8;
     } else if (layer == 1) {     // [J][own: [32 slabs][128 x 16] | shipped: [2 halves][32 slabs][64 x 16]]; k in my half
-      const int J = (int)(r / 65536), rr0 = (int)(r % 65536);
+      // blocks in the order CTA p consumes them: pair m = [shipped chunk 2 m + 1 - p][own chunk 2 m + p]
+      const int blk = (int)(r / 65536), rr0 = (int)(r % 65536);
+      const int J = (blk & 1) ? 2 * (blk >> 1) + p : 2 * (blk >> 1) + 1 - p;
       if ((J & 1) == p) {
         const int slab = rr0 / 2048, rr = rr0 % 2048;
         n = 128 * J + (rr / 128) * 8 + (rr % 64) / 8;

@@ -217,6 +217,10 @@ __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.ac
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// the same without release semantics: for "I have finished READING" hand-offs, issued after the consumers of those loads
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -245,6 +249,10 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster_addr, const void* 
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
                "r"(smem_u32(src_smem)), "r"(bytes), "r"(mbar_cluster_addr)
                : "memory");
+}
+// asynchronous L2 prefetch of a contiguous global range (size a multiple of 16 bytes)
+__device__ __forceinline__ void prefetch_l2(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources read
