@@ -340,7 +340,10 @@ def run_ours(a):
         p.requires_grad_(False)
     model.component, model.all_trained = C - 1, False
     model.pack_all()
-    ops = gd.KernelOps(model)
+    peer = world > 1 and not a.nccl
+    ops = gd.KernelOps(model, peer=peer)
+    if peer:    # library-owned peer-memory exchange over NVLink (gbnf_comm_*): no NCCL call inside a step
+        gd.init_peer_exchange(model, a.batch)
     nb = a.rows // a.batch
     batches = [x_all[i * a.batch:(i + 1) * a.batch] for i in range(nb)]
 
@@ -464,6 +467,8 @@ def run_ours(a):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = job_rows * a.steps / (e2e_ms.item() * 1e-3)
 
+    if peer:
+        gd.shutdown_peer_exchange(model)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -486,8 +491,8 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "batch": a.batch, "rows_resident_per_gpu": a.rows, "gemm_mode": a.mode,
                    "l2": f"resident rows {a.rows * D * 4 / 1e6:.0f} MB per GPU > 126 MB L2; batches rotate through them",
                    "parallelism": (f"component-parallel x{world} ({C // world} of {C} components per GPU, every GPU sees all "
-                                   f"{a.batch} rows of a step; one NCCL all-gather of [B, C/G] log q per step)" if comp_par else
-                                   f"batch-parallel x{world} (weak: {a.batch} rows per GPU per step)")},
+                                   f"{a.batch} rows of a step; log q [B, C/G] " + ("stored by the coupling epilogue into every rank's gather buffer over NVLink peer memory" if peer else "all-gathered with NCCL") + ")" if comp_par else
+                                   f"batch-parallel x{world} (weak: {a.batch} rows per GPU per step; global softmax via " + ("the library's peer-memory exchange" if peer else "three NCCL scalar all-reduces") + ")")},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "coupling (C/G components) + all-gather + mixture" if comp_par else "fused coupling+mixture", "kernel_ms": k_ms, "weights_ms": w_ms,
                      "flops_per_sample": flops_per_sample(cfg),
@@ -520,6 +525,8 @@ def main():
     p.add_argument("--rows", type=int, default=1 << 20)
     p.add_argument("--cpu-rows", type=int, default=524288)
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--nccl", action="store_true", help="N > 1: torch.distributed collectives between the staged kernels instead of "
+                   "the library's peer-memory exchange (A/B measurements)")
     p.add_argument("--port", action="store_true", help="--impl reference: time the oracle's torch-CPU port even when baseline/_ref exists")
     a = p.parse_args()
     a.warmup = max(a.warmup, 3)

@@ -63,6 +63,11 @@ SIGNATURES = {
     "gbnf_weight_stats": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "gbnf_weight_apply": (C.c_int, [_vp, _vp, _i64, _vp, _f32, _f32, _i32, _vp, _vp, _vp]),
     "gbnf_weight_renorm": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),
+    "gbnf_comm_local_handle": (C.c_int, [_vp, _i64, _vp]),
+    "gbnf_comm_init": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "gbnf_comm_destroy": (C.c_int, [_vp]),
+    "gbnf_boost_weights_dist": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _i32, _vp, _vp, _vp]),
+    "gbnf_mixture_component_parallel": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp]),
     "gbnf_resample": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "gbnf_gather_rows": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "gbnf_actnorm_init": (C.c_int, [_vp, _i64, _i32, C.c_float, _vp, _vp, _vp]),

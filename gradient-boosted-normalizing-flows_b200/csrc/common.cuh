@@ -9,6 +9,7 @@ namespace gbnf {
 
 constexpr int kMaxComponents = 256;   // coef table in shared memory
 constexpr int kMaxD = 256;
+constexpr int kMaxRanks = 8;            // GPUs of one node that can share an exchange (gbnf_comm_init)
 constexpr int kEpPad = 64;             // padded length of the gather-order step tables
 
 // ---- packed parameter layout ---------------------------------------------------------------------------
@@ -79,12 +80,50 @@ struct CouplingArgs {
   int split, comps_per_unit, num_units;
   float* lse_terms;                // [num_tiles * 128][n_mix]
   unsigned int* tile_ctr;          // [num_tiles], zero between launches (reset by the last arriver)
+  // component-parallel multi-GPU (gbnf_mixture_component_parallel): when n_peers > 0 every log q value is ALSO stored into the
+  // gather buffer of every rank (peer memory over NVLink) at column peer_col0 + (c - c0) of a [B, peer_ld] matrix
+  float* logq_peers[kMaxRanks];
+  int n_peers, peer_ld, peer_col0;
   int exp_flags;                   // experiments (GBNF_EXP env, diagnostics only): bit 0 = producer skips the weight copies
   int* error_flag;                 // status words in MAPPED HOST memory (the host can read them after a trap, without a
                                    // synchronisation): [0] watchdog code of a timed-out wait, [1] fp16 weight overflow (pack),
                                    // [2] a value entering an fp16 GEMM operand was not finite in fp16
   long long* prof;                 // optional cycle counters (CTA 0), see gbnf_get_profile
 };
+
+// ---- peer-memory exchange between the ranks of one node (one process per GPU; gbnf_comm_init) ---------------------------------
+// Every rank owns one CommBlock in its own HBM, exported with cudaIpcGetMemHandle and mapped by all peers.  A rank PUBLISHES a
+// value by storing it into slot [parity][its rank] of EVERY rank's block (plain stores over NVLink), then a system-scope fence,
+// then the epoch number into the matching flag word; a rank CONSUMES by spinning on the flags of its OWN block (local L2) until
+// they show the current epoch.  Slots are double buffered by epoch parity: a rank cannot run two epochs ahead of a peer, because
+// passing epoch e + 1's wait needs the peer's e + 1 value, which the peer only publishes after all its epoch-e reads.
+struct CommBlock {
+  float ms[2][kMaxRanks][2];              // batch softmax statistics (max, sum exp) of each rank's row shard
+  unsigned int ms_flag[2][kMaxRanks];
+  double wsum[2][kMaxRanks];              // sum of the (clamped) weights of each rank's row shard
+  unsigned int ws_flag[2][kMaxRanks];
+  unsigned int done_flag[2][kMaxRanks];   // component-parallel: rank r has written its log q block into everybody's gather buffer
+};
+struct CommView {
+  CommBlock* blk[kMaxRanks];              // blk[r]: rank r's block (blk[rank] is local)
+  float* gather[kMaxRanks];               // gather[r]: rank r's [2][cap_rows * ld] log q gather buffers
+  long long gather_stride;                // floats per parity buffer
+  int rank, world;
+  unsigned int epoch;
+};
+constexpr long long kCommSpinLimit = 4000000000LL;   // ~2 s: a missing peer must not hang the GPU
+__device__ __forceinline__ void comm_wait_flag(const unsigned int* flag, unsigned int epoch, int* status) {
+  const volatile unsigned int* f = flag;
+  if (*f == epoch) return;
+  const long long t0 = clock64();
+  while (*f != epoch) {
+    if (clock64() - t0 > kCommSpinLimit) {
+      if (status) *reinterpret_cast<volatile int*>(status) = 40;
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
 
 // ---- device helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_max(float v) {

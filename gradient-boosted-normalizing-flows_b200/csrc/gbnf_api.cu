@@ -94,7 +94,17 @@ struct gbnf_ctx {
   int profiling = 0;             // GBNF_PROF=1: cycle counters + event trace, 2: event trace only (gbnf_get_profile / _trace)
   int last_grid = 0;
   long long launches = 0;
+  // peer-memory exchange (gbnf_comm_*): one allocation = CommBlock (4 KB) + 2 parity gather buffers [comm_rows x C] floats
+  void* comm_mem = nullptr;
+  void* comm_peer_mem[kMaxRanks] = {};
+  long long comm_rows = 0;
+  bool comm_ready = false;
+  CommView cv{};
+  float* cp_tmp = nullptr;       // component-parallel fallback: local log q block before the scatter kernel
+  long long cp_tmp_cap = 0;
 };
+constexpr size_t kCommBlockBytes = 4096;
+static_assert(sizeof(CommBlock) <= kCommBlockBytes, "CommBlock does not fit its slot");
 
 namespace {
 
@@ -110,6 +120,7 @@ const char* watchdog_text(int code) {
     case 30: return "epilogue waiting for a layer-1 accumulator";
     case 31: return "epilogue waiting for a layer-2 accumulator";
     case 32: return "epilogue waiting for the last-layer accumulator";
+    case 40: return "waiting for a peer rank's value in the exchange block (a rank is missing or out of step)";
     default: return "in-kernel wait";
   }
 }
@@ -258,7 +269,8 @@ int ensure_scan_workspace(gbnf_ctx* h, long long B) {
 }
 
 int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, float* logq, int ld_logq, float* z_out,
-                    float* ldj_out, const float* rho, int n_mix, int skip_c, int mix_mode, float* G_ll, cudaStream_t st) {
+                    float* ldj_out, const float* rho, int n_mix, int skip_c, int mix_mode, float* G_ll, cudaStream_t st,
+                    bool to_peers = false, int peer_ld = 0, int peer_col0 = 0) {
   for (int c = c0; c < c1; ++c)
     if (!h->packed[c]) return fail(GBNF_ERR_STATE, "component " + std::to_string(c) + " has not been packed");
   if (B == 0) return GBNF_OK;
@@ -270,7 +282,7 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
       const long long nb = std::min(kMaxRowsPerLaunch, B - r0);
       int rc = launch_coupling(h, x + r0 * h->md.D, nb, c0, c1, logq ? logq + r0 * ld_logq : nullptr, ld_logq,
                                z_out ? z_out + r0 * h->md.D : nullptr, ldj_out ? ldj_out + r0 : nullptr, rho, n_mix, skip_c,
-                               mix_mode, G_ll ? G_ll + r0 : nullptr, st);
+                               mix_mode, G_ll ? G_ll + r0 : nullptr, st, false, 0, 0);
       if (rc != GBNF_OK) return rc;
     }
     return GBNF_OK;
@@ -281,6 +293,10 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
   a.steps = h->steps_d; a.comps = h->comps_d; a.fblob = h->fblob; a.iblob = h->iblob; a.wblob = h->wblob; a.md = h->md;
   a.cc_off = h->cc_off;
   a.error_flag = h->flags;
+  if (to_peers) {
+    a.n_peers = h->cv.world; a.peer_ld = peer_ld; a.peer_col0 = peer_col0;
+    for (int q = 0; q < h->cv.world; ++q) a.logq_peers[q] = h->cv.gather[q] + (h->cv.epoch & 1u) * h->cv.gather_stride;
+  }
   { const char* ee = std::getenv("GBNF_EXP"); a.exp_flags = ee ? std::atoi(ee) : 0; }
   a.prof = h->prof;
   const int R = h->rows_per_cta;
@@ -381,8 +397,8 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   CREATE_TRY(cudaMemset(h->fblob, 0, std::max(1LL, h->f_count) * sizeof(float)));
   CREATE_TRY(cudaMalloc(&h->step_params_d, (size_t)c.K * sizeof(gbnf_step_params)));
   CREATE_TRY(cudaMalloc(&h->partial, (size_t)h->num_sms * 8 * 2 * sizeof(float)));
-  CREATE_TRY(cudaMalloc(&h->ticket, sizeof(unsigned int)));
-  CREATE_TRY(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
+  CREATE_TRY(cudaMalloc(&h->ticket, 2 * sizeof(unsigned int)));
+  CREATE_TRY(cudaMemset(h->ticket, 0, 2 * sizeof(unsigned int)));
   CREATE_TRY(cudaMalloc(&h->ms, 2 * sizeof(float)));
   CREATE_TRY(cudaMalloc(&h->wsum, sizeof(double)));
   CREATE_TRY(cudaHostAlloc((void**)&h->flags_host, 4 * sizeof(int), cudaHostAllocMapped));
@@ -417,6 +433,7 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
 
 void gbnf_destroy(gbnf_handle h) {
   if (!h) return;
+  gbnf_comm_destroy(h);
   DeviceGuard guard_(h->cfg.device);
   cudaFree(h->base_mean); cudaFree(h->base_scale);
   if (h->flags_host) cudaFreeHost(h->flags_host);
@@ -570,7 +587,7 @@ int gbnf_mixture_logdensity(gbnf_handle h, const float* d_logq, int64_t B, int32
     return GBNF_OK;
   }
   mixture_lse_kernel<<<grid_for(h, B, kMixThreads), kMixThreads, 0, (cudaStream_t)stream>>>(d_logq, B, ld, n_comp, d_rho,
-                                                                                         skip_c, mix_mode, d_G_ll);
+                                                                                         skip_c, mix_mode, d_G_ll, CommView{}, h->flags);
   h->launches++;
   CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
@@ -600,7 +617,7 @@ int gbnf_weight_stats(gbnf_handle h, const float* d_G_ll, int64_t B, float* d_ms
   if (!h || !d_G_ll || !d_ms || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
   ENTER(h);
   softmax_stats_kernel<<<grid_for(h, B, kMixThreads * 4), kMixThreads, 0, (cudaStream_t)stream>>>(d_G_ll, B, h->partial,
-                                                                                              h->ticket, d_ms);
+                                                                                              h->ticket, d_ms, CommView{});
   h->launches++;
   CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
@@ -614,7 +631,7 @@ int gbnf_weight_apply(gbnf_handle h, const float* d_G_ll, int64_t B, const float
   cudaStream_t st = (cudaStream_t)stream;
   zero_double_kernel<<<1, 1, 0, st>>>(d_wsum);
   weight_apply_kernel<<<grid_for(h, B, kMixThreads * 4), kMixThreads, 0, st>>>(d_G_ll, B, d_ms, clamp_lo, clamp_hi, d_w,
-                                                                             d_wsum, nullptr);
+                                                                             d_wsum, nullptr, CommView{}, h->ticket + 1, h->flags);
   h->launches += 2;
   CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
@@ -624,7 +641,7 @@ int gbnf_weight_renorm(gbnf_handle h, float* d_w, int64_t B, const double* d_wsu
   if (!h || !d_w || !d_wsum || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
   ENTER(h);
   weight_renorm_kernel<<<grid_for(h, B, kMixThreads * 4), kMixThreads, 0, (cudaStream_t)stream>>>(
-      d_w, B, d_wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, nullptr);
+      d_w, B, d_wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, nullptr, CommView{}, h->flags);
   h->launches++;
   CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
@@ -637,11 +654,122 @@ int gbnf_boost_weights(gbnf_handle h, const float* d_G_ll, int64_t B, float clam
   ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   const int g = grid_for(h, B, kMixThreads * 4);
-  softmax_stats_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->partial, h->ticket, h->ms);
+  softmax_stats_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->partial, h->ticket, h->ms, CommView{});
   zero_double_kernel<<<1, 1, 0, st>>>(h->wsum);
-  weight_apply_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->ms, clamp_lo, clamp_hi, d_w, h->wsum, d_stats);
-  weight_renorm_kernel<<<g, kMixThreads, 0, st>>>(d_w, B, h->wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, d_stats);
+  weight_apply_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->ms, clamp_lo, clamp_hi, d_w, h->wsum, d_stats, CommView{}, h->ticket + 1, h->flags);
+  weight_renorm_kernel<<<g, kMixThreads, 0, st>>>(d_w, B, h->wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, d_stats, CommView{}, h->flags);
   h->launches += 4;
+  CUDA_TRY_H(h, cudaGetLastError());
+  return GBNF_OK;
+}
+
+// ---- multi-GPU: peer-memory exchange over NVLink (one process per GPU; handles exchanged by the caller's plumbing) ---------------
+int gbnf_comm_local_handle(gbnf_handle h, int64_t max_rows, void* out_handle64) {
+  if (!h || !out_handle64 || max_rows < 0) return fail(GBNF_ERR_INVALID, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  ENTER(h);
+  if (h->comm_ready) return fail(GBNF_ERR_STATE, "the exchange is already initialised (gbnf_comm_destroy first)");
+  if (h->comm_mem) { cudaFree(h->comm_mem); h->comm_mem = nullptr; }
+  const long long rows = std::max<long long>(max_rows, 1);
+  const size_t bytes = kCommBlockBytes + 2ull * (size_t)rows * h->cfg.C * sizeof(float);
+  CUDA_TRY_H(h, cudaMalloc(&h->comm_mem, bytes));
+  CUDA_TRY_H(h, cudaMemset(h->comm_mem, 0, bytes));
+  CUDA_TRY_H(h, cudaDeviceSynchronize());
+  h->comm_rows = rows;
+  cudaIpcMemHandle_t ipc;
+  CUDA_TRY_H(h, cudaIpcGetMemHandle(&ipc, h->comm_mem));
+  std::memcpy(out_handle64, &ipc, 64);
+  return GBNF_OK;
+}
+
+int gbnf_comm_init(gbnf_handle h, int32_t rank, int32_t world, const void* all_handles) {
+  if (!h || !all_handles || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(GBNF_ERR_INVALID, "bad rank / world (<= 8)");
+  if (!h->comm_mem) return fail(GBNF_ERR_STATE, "call gbnf_comm_local_handle first");
+  ENTER(h);
+  CommView cv{};
+  cv.rank = rank; cv.world = world; cv.epoch = 0;
+  cv.gather_stride = h->comm_rows * h->cfg.C;
+  for (int r = 0; r < world; ++r) {
+    void* base = h->comm_mem;
+    if (r != rank) {
+      cudaIpcMemHandle_t ipc;
+      std::memcpy(&ipc, (const char*)all_handles + 64 * r, 64);
+      CUDA_TRY_H(h, cudaIpcOpenMemHandle(&base, ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->comm_peer_mem[r] = base;
+    }
+    cv.blk[r] = reinterpret_cast<CommBlock*>(base);
+    cv.gather[r] = reinterpret_cast<float*>((char*)base + kCommBlockBytes);
+  }
+  h->cv = cv;
+  h->comm_ready = true;
+  return GBNF_OK;
+}
+
+int gbnf_comm_destroy(gbnf_handle h) {
+  if (!h) return fail(GBNF_ERR_INVALID, "null handle");
+  DeviceGuard guard_(h->cfg.device);
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (h->comm_peer_mem[r]) { cudaIpcCloseMemHandle(h->comm_peer_mem[r]); h->comm_peer_mem[r] = nullptr; }
+  if (h->comm_mem) { cudaFree(h->comm_mem); h->comm_mem = nullptr; }
+  if (h->cp_tmp) { cudaFree(h->cp_tmp); h->cp_tmp = nullptr; h->cp_tmp_cap = 0; }
+  h->comm_ready = false;
+  h->cv = CommView{};
+  return GBNF_OK;
+}
+
+int gbnf_boost_weights_dist(gbnf_handle h, const float* d_G_ll, int64_t B, float clamp_lo, float clamp_hi, int32_t mode,
+                            float* d_w, float* d_stats, void* stream) {
+  if (!h || !d_G_ll || !d_w || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument (every rank needs at least one row)");
+  if (mode != GBNF_WEIGHTS_DENSITY && mode != GBNF_WEIGHTS_TOY) return fail(GBNF_ERR_INVALID, "bad weights mode");
+  if (!h->comm_ready) return fail(GBNF_ERR_STATE, "gbnf_comm_init has not been called");
+  ENTER(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->cv.epoch += 1;
+  const int g = grid_for(h, B, kMixThreads * 4);
+  softmax_stats_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->partial, h->ticket, h->ms, h->cv);
+  zero_double_kernel<<<1, 1, 0, st>>>(h->wsum);
+  weight_apply_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->ms, clamp_lo, clamp_hi, d_w, h->wsum, d_stats, h->cv, h->ticket + 1, h->flags);
+  weight_renorm_kernel<<<g, kMixThreads, 0, st>>>(d_w, B, h->wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, d_stats, h->cv, h->flags);
+  h->launches += 4;
+  CUDA_TRY_H(h, cudaGetLastError());
+  return GBNF_OK;
+}
+
+int gbnf_mixture_component_parallel(gbnf_handle h, const float* d_x, int64_t B, int32_t n_comp, const float* d_rho, int32_t skip_c,
+                                    int32_t mix_mode, float* d_G_ll, void* stream) {
+  if (!h || !d_x || !d_rho || !d_G_ll || B <= 0) return fail(GBNF_ERR_INVALID, "bad argument");
+  if (!h->comm_ready) return fail(GBNF_ERR_STATE, "gbnf_comm_init has not been called");
+  const int world = h->cv.world, rank = h->cv.rank;
+  if (n_comp < world || n_comp > h->cfg.C || n_comp % world != 0)
+    return fail(GBNF_ERR_INVALID, "component-parallel evaluation needs n_comp to be a positive multiple of the world size");
+  if (B > h->comm_rows) return fail(GBNF_ERR_INVALID, "batch larger than the gather buffer given to gbnf_comm_local_handle");
+  if (skip_c == 0) return fail(GBNF_ERR_INVALID, "skip_c == 0 is not reachable in the reference (toy_experiment.py:409)");
+  if (mix_mode != GBNF_MIX_SIMPLEX && mix_mode != GBNF_MIX_RAW_RHO) return fail(GBNF_ERR_INVALID, "bad mix_mode");
+  ENTER(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->cv.epoch += 1;
+  const int per = n_comp / world, c0 = rank * per;
+  const int ld = h->cfg.C;                                  // gather buffers are [rows, C]
+  if (h->cfg.gemm_mode != GBNF_GEMM_FP32 && (h->tc2 || h->tc3)) {
+    // fused: the coupling kernel's epilogue stores log q into every rank's gather buffer
+    int rc = launch_coupling(h, d_x, B, c0, c0 + per, nullptr, per, nullptr, nullptr, nullptr, 0, -1, 0, nullptr, st, true, ld, c0);
+    if (rc != GBNF_OK) return rc;
+  } else {
+    const long long need = (long long)B * per;
+    if (need > h->cp_tmp_cap) {
+      if (h->cp_tmp) cudaFree(h->cp_tmp);
+      h->cp_tmp = nullptr; h->cp_tmp_cap = 0;
+      CUDA_TRY_H(h, cudaMalloc(&h->cp_tmp, need * sizeof(float)));
+      h->cp_tmp_cap = need;
+    }
+    int rc = launch_coupling(h, d_x, B, c0, c0 + per, h->cp_tmp, per, nullptr, nullptr, nullptr, 0, -1, 0, nullptr, st);
+    if (rc != GBNF_OK) return rc;
+    comm_scatter_logq_kernel<<<grid_for(h, need, kMixThreads), kMixThreads, 0, st>>>(h->cp_tmp, B, per, h->cv, ld, c0);
+    h->launches++;
+  }
+  const float* mine = h->cv.gather[rank] + (h->cv.epoch & 1u) * h->cv.gather_stride;
+  mixture_lse_kernel<<<grid_for(h, B, kMixThreads), kMixThreads, 0, st>>>(mine, B, ld, n_comp, d_rho, skip_c, mix_mode, d_G_ll, h->cv, h->flags);
+  h->launches++;
   CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }

@@ -50,11 +50,24 @@ __device__ __forceinline__ void mixture_rows_small(const float* __restrict__ log
 // ---- G_ll[b] = logsumexp_c(coef[c] + logq[b, c]) ---------------------------------------------------------
 // One thread per row; a warp reads 32 consecutive rows = one contiguous span of 32*ld floats.  With ld % 4 == 0
 // the row is fetched with 128-bit loads.
+// With cv.world > 1 (component-parallel) logq is this rank's gather buffer: block 0 first publishes "my block is written"
+// (the coupling launch before this one in the stream stored it into every rank's buffer), every block then waits until all
+// ranks have published the current epoch.
 __global__ void __launch_bounds__(kMixThreads) mixture_lse_kernel(const float* __restrict__ logq, long long B, int ld,
                                                                  int n, const float* __restrict__ rho, int skip_c,
-                                                                 int mix_mode, float* __restrict__ G_ll) {
+                                                                 int mix_mode, float* __restrict__ G_ll, CommView cv, int* status) {
   __shared__ float coef[kMaxComponents];
   __shared__ float rho_sum;
+  if (cv.world > 1) {
+    const int par = cv.epoch & 1u;
+    if (blockIdx.x == 0 && threadIdx.x < cv.world) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned int*>(&cv.blk[threadIdx.x]->done_flag[par][cv.rank]) = cv.epoch;
+    }
+    if (threadIdx.x < cv.world) comm_wait_flag(&cv.blk[cv.rank]->done_flag[par][threadIdx.x], cv.epoch, status);
+    __syncthreads();
+    __threadfence_system();
+  }
   if (threadIdx.x == 0) {
     if (mix_mode == GBNF_MIX_GEOMETRIC) {
       // utils/density_plotting.py:199-226: total += log_prob_c * rho_c over the components with rho_c != 0, then / sum(rho[0:n])
@@ -150,7 +163,7 @@ __device__ inline MsPair ms_block_reduce(MsPair v, MsPair* sm /* [32] */) {
 __global__ void __launch_bounds__(kMixThreads) softmax_stats_kernel(const float* __restrict__ G_ll, long long B,
                                                                    float* __restrict__ partial /* [grid][2] */,
                                                                    unsigned int* __restrict__ ticket,
-                                                                   float* __restrict__ ms_out /* [2] */) {
+                                                                   float* __restrict__ ms_out /* [2] */, CommView cv) {
   __shared__ MsPair sm[32];
   __shared__ bool is_last;
   // thread-local online (max, sum) over a strided slice, ONE sweep (G_ll is read from HBM once whatever its size): the
@@ -195,6 +208,19 @@ __global__ void __launch_bounds__(kMixThreads) softmax_stats_kernel(const float*
     }
     MsPair f = ms_block_reduce(w, sm);
     if (threadIdx.x == 0) { ms_out[0] = f.m; ms_out[1] = f.s; *ticket = 0u; }
+    if (cv.world > 1) {   // publish this shard's (max, sum exp) into every rank's block
+      __shared__ float pub[2];
+      if (threadIdx.x == 0) { pub[0] = f.m; pub[1] = f.s; }
+      __syncthreads();
+      if (threadIdx.x < cv.world) {
+        CommBlock* b = cv.blk[threadIdx.x];
+        const int par = cv.epoch & 1u;
+        b->ms[par][cv.rank][0] = pub[0];
+        b->ms[par][cv.rank][1] = pub[1];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(&b->ms_flag[par][cv.rank]) = cv.epoch;
+      }
+    }
   }
 }
 
@@ -205,9 +231,26 @@ __global__ void __launch_bounds__(kMixThreads) softmax_stats_kernel(const float*
 __global__ void __launch_bounds__(kMixThreads) weight_apply_kernel(const float* __restrict__ G_ll, long long B,
                                                                   const float* __restrict__ ms, float lo, float hi,
                                                                   float* __restrict__ w, double* __restrict__ wsum,
-                                                                  float* __restrict__ stats_opt) {
+                                                                  float* __restrict__ stats_opt, CommView cv, unsigned int* ticket,
+                                                                  int* status) {
   __shared__ double sm[32];
-  const float M = ms[0], S = ms[1];
+  __shared__ float gms[2];
+  if (cv.world > 1) {
+    // GLOBAL batch softmax: every block of every rank merges the ranks' (max, sum exp) pairs in rank order -> identical bits
+    if (threadIdx.x < cv.world) comm_wait_flag(&cv.blk[cv.rank]->ms_flag[cv.epoch & 1u][threadIdx.x], cv.epoch, status);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const volatile float* v = &cv.blk[cv.rank]->ms[cv.epoch & 1u][0][0];
+      float Mg = -INFINITY;
+      for (int r = 0; r < cv.world; ++r) Mg = fmaxf(Mg, v[2 * r]);
+      float Sg = 0.f;
+      for (int r = 0; r < cv.world; ++r) { const float mr = v[2 * r]; if (mr != -INFINITY) Sg += v[2 * r + 1] * expf(mr - Mg); }
+      gms[0] = Mg; gms[1] = Sg;
+    }
+    __syncthreads();
+  }
+  const float M = (cv.world > 1) ? gms[0] : ms[0], S = (cv.world > 1) ? gms[1] : ms[1];
   const float wmax = 1.0f / S;
   const bool clamp = wmax > hi;
   double acc = 0.0;
@@ -250,12 +293,46 @@ __global__ void __launch_bounds__(kMixThreads) weight_apply_kernel(const float* 
   if (stats_opt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     stats_opt[0] = M; stats_opt[1] = S; stats_opt[2] = clamp ? 1.f : 0.f;
   }
+  if (cv.world > 1) {   // the last block to finish publishes this shard's sum of weights into every rank's block
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      if (threadIdx.x == 0) *ticket = 0u;
+      if (threadIdx.x < cv.world) {
+        const double local = *reinterpret_cast<volatile double*>(wsum);
+        CommBlock* b = cv.blk[threadIdx.x];
+        const int par = cv.epoch & 1u;
+        b->wsum[par][cv.rank] = local;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(&b->ws_flag[par][cv.rank]) = cv.epoch;
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kMixThreads) weight_renorm_kernel(float* __restrict__ w, long long B,
                                                                    const double* __restrict__ wsum, int always,
-                                                                   float* __restrict__ stats_opt) {
-  const float s = (float)(*wsum);
+                                                                   float* __restrict__ stats_opt, CommView cv, int* status) {
+  __shared__ double gsum;
+  if (cv.world > 1) {   // global sum of weights = the ranks' sums added in rank order (identical on every rank)
+    if (threadIdx.x < cv.world) comm_wait_flag(&cv.blk[cv.rank]->ws_flag[cv.epoch & 1u][threadIdx.x], cv.epoch, status);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const volatile double* v = &cv.blk[cv.rank]->wsum[cv.epoch & 1u][0];
+      double t = 0.0;
+      for (int r = 0; r < cv.world; ++r) t += v[r];
+      gsum = t;
+    }
+    __syncthreads();
+  }
+  const float s = (cv.world > 1) ? (float)gsum : (float)(*wsum);
   if (stats_opt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) stats_opt[3] = s;
   if (!always && s == 1.0f) return;            // `if weights.sum() != 1.0` density_experiment.py:640 (toy: always)
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -273,6 +350,19 @@ __global__ void __launch_bounds__(kMixThreads) weight_renorm_kernel(float* __res
 }
 
 __global__ void zero_double_kernel(double* p) { *p = 0.0; }
+
+// Component-parallel fallback for the coupling kernels that do not store into peer memory themselves: copies this rank's
+// log q block [B, nc] into columns [col0, col0 + nc) of every rank's [B, ld] gather buffer.
+__global__ void __launch_bounds__(kMixThreads) comm_scatter_logq_kernel(const float* __restrict__ local, long long B, int nc, CommView cv,
+                                                                       int ld, int col0) {
+  float* const base_off = nullptr; (void)base_off;
+  const long long total = B * nc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nc; const int c = (int)(i - r * nc);
+    const float v = local[i];
+    for (int q = 0; q < cv.world; ++q) cv.gather[q][(cv.epoch & 1u) * cv.gather_stride + r * ld + col0 + c] = v;
+  }
+}
 
 // ---- inverse-CDF resampling: fp64 inclusive scan of w, then left binary search per uniform ---------------------
 constexpr int kScanThreads = 256;

@@ -11,6 +11,13 @@ The reference is single-process (no distributed code at all), so this 
 
 The per-rank compute goes through an `ops` object so that the collective algebra can be exercised on CPU with the
 gloo backend (tests/test_dist_gloo.py substitutes the oracle there); the product default is KernelOps = the C ABI.
+
+Data path of the product (KernelOps after `init_peer_exchange`): NO NCCL call per step.  The library owns the exchange
+(include/gbnf.h, gbnf_comm_*): every rank maps every other rank's exchange block (cudaIpc, peer memory over NVLink); the
+weight kernels publish / consume the two batch reductions inside the kernels themselves, and the coupling kernel's epilogue
+stores log q straight into every rank's gather buffer.  torch.distributed only carries the one-time handle exchange and the
+barriers around set-up / tear-down.  Without `init_peer_exchange` the same functions fall back to torch.distributed
+collectives between the staged kernels (three scalar all-reduces / one all-gather) -- the algebra the gloo tests cover.
 """
 import ctypes as C
 
@@ -33,12 +40,63 @@ def shard_components(n_comp, world, rank):
     return list(range(start, stop))
 
 
-class KernelOps:
-    """Per-rank compute through libgbnf_b200.so (device tensors in, device tensors out)."""
+def init_peer_exchange(model, max_rows, group=None):
+    """One-time set-up of the library-owned exchange: allocate this rank's block (+ gather buffers for `max_rows` rows),
+    all-gather the 64-byte cudaIpc handles, map the peers (gbnf_comm_init), barrier."""
+    world, rank = _world(group)
+    lib = _lib.load()
+    dev = model.rho.device
+    h = model.handle(dev)
+    mine = (C.c_ubyte * 64)()
+    _lib.check(lib.gbnf_comm_local_handle(h, int(max_rows), mine))
+    t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+    allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+    if world > 1:
+        dist.all_gather_into_tensor(allh, t, group=group)
+    else:
+        allh.copy_(t)
+    arr = (C.c_ubyte * (64 * world))(*allh.cpu().tolist())
+    _lib.check(lib.gbnf_comm_init(h, rank, world, arr))
+    if world > 1:
+        dist.barrier(group=group)
+    return True
 
-    def __init__(self, model):
+
+def shutdown_peer_exchange(model, group=None):
+    """Barrier (peers must have stopped writing into this rank's block), then unmap and free."""
+    world, _ = _world(group)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(group=group)
+    if model._handle is not None:
+        _lib.check(_lib.load().gbnf_comm_destroy(model._handle))
+
+
+class KernelOps:
+    """Per-rank compute through libgbnf_b200.so (device tensors in, device tensors out).  peer=True: the library's own
+    peer-memory exchange is initialised (init_peer_exchange) and the *_dist entry points are used."""
+
+    def __init__(self, model, peer=False):
         self.model = model
         self.lib = _lib.load()
+        self.peer = peer
+
+    def boost_weights_dist(self, G_ll, mode, batch_size):
+        w = torch.empty_like(G_ll)
+        lo = 0.01 if mode == "density" else 0.1 / float(batch_size)
+        _lib.check(self.lib.gbnf_boost_weights_dist(self._h(G_ll), self._p(G_ll), G_ll.shape[0], lo, 0.1, _lib.WEIGHTS[mode],
+                                                    self._p(w), None, self._s(G_ll)))
+        return w
+
+    def mixture_component_parallel(self, x, n_comp, skip_c=-1):
+        for c in range(n_comp):
+            self.model.pack_component(c)
+        G = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+        rho = self.model.rho.detach().to(x.device, torch.float32).contiguous()
+        _lib.check(self.lib.gbnf_mixture_component_parallel(self._h(x), self._p(x), x.shape[0], n_comp, self._p(rho), skip_c,
+                                                            _lib.MIX_SIMPLEX, self._p(G), self._s(x)))
+        return G
 
     def _h(self, t):
         return self.model.handle(t.device)
@@ -102,6 +160,8 @@ def boosting_weights_batch_parallel(ops, G_ll_local, mode="density", batch_size=
     """Weights of this rank's row shard under the GLOBAL batch softmax (density_experiment.py:627-641 semantics on the
     union of all shards).  `batch_size` (toy clamp floor 0.1 / batch_size) is the global batch size."""
     n_local = G_ll_local.shape[0]
+    if getattr(ops, "peer", False):      # library-owned exchange through peer memory: no collective call on the data path
+        return ops.boost_weights_dist(G_ll_local, mode, batch_size)
     if n_local > 0:
         ms = ops.weight_stats(G_ll_local)
     else:
@@ -126,6 +186,8 @@ def mixture_component_parallel(ops, x, n_comp, skip_c=-1, group=None):
     world, rank = _world(group)
     if world == 1:
         return ops.mixture(ops.component_logq(x, 0, n_comp), n_comp, skip_c)
+    if getattr(ops, "peer", False):      # coupling epilogue stores log q into every rank's gather buffer (NVLink peer memory)
+        return ops.mixture_component_parallel(x, n_comp, skip_c)
     if n_comp % world != 0:
         raise ValueError("component-parallel evaluation needs n_comp % world_size == 0")
     per = n_comp // world

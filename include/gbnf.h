@@ -173,6 +173,30 @@ int gbnf_weight_apply(gbnf_handle h, const float* d_G_ll, int64_t B, const float
                       float clamp_hi, int32_t mode, float* d_w, double* d_wsum, void* stream);
 int gbnf_weight_renorm(gbnf_handle h, float* d_w, int64_t B, const double* d_wsum, int32_t mode, void* stream);
 
+/* ---- multi-GPU on one node: one process per GPU, values exchanged through PEER MEMORY over NVLink ------------
+ * The reference has no distributed code; this is the library-owned collective SURVEY 8(b) lists as
+ * gbnf_comm_init.  No NCCL call sits on the data path: a rank publishes a value by storing it into every rank's
+ * exchange block (cudaIpc-mapped device memory) followed by a flag word, and consumes by spinning on its own block
+ * inside the kernel that needs the value (bounded: a missing peer raises watchdog code 40 after ~2 s).
+ *   1. every rank: gbnf_comm_local_handle(h, max_rows, handle64)   allocates its block (+ a [2][max_rows, C] gather buffer
+ *      for the component-parallel layout) and returns the 64-byte cudaIpcMemHandle_t;
+ *   2. the caller all-gathers the handles with whatever plumbing it has (torch.distributed in gbnf_b200/dist.py);
+ *   3. every rank: gbnf_comm_init(h, rank, world, handles[world][64]); a barrier; then, in the SAME order on every rank:
+ *   gbnf_boost_weights_dist          batch-parallel: this rank's rows, boosting weights under the GLOBAL batch softmax
+ *                                    (density_experiment.py:627-641 on the union of all shards); every rank merges the
+ *                                    ranks' (max, sum exp) and sum-of-weights in rank order -> bitwise identical scalars
+ *   gbnf_mixture_component_parallel  component-parallel: rank g evaluates components [g n/G, (g+1) n/G) of ALL rows, the
+ *                                    coupling kernel's epilogue stores log q straight into every rank's gather buffer,
+ *                                    the mixture kernel waits for all blocks (density_experiment.py:612-622)
+ *   gbnf_comm_destroy (after a barrier: peers must have stopped writing). world <= 8. */
+int gbnf_comm_local_handle(gbnf_handle h, int64_t max_rows, void* out_handle64);
+int gbnf_comm_init(gbnf_handle h, int32_t rank, int32_t world, const void* all_handles);
+int gbnf_comm_destroy(gbnf_handle h);
+int gbnf_boost_weights_dist(gbnf_handle h, const float* d_G_ll, int64_t B, float clamp_lo, float clamp_hi, int32_t mode,
+                            float* d_w, float* d_stats, void* stream);
+int gbnf_mixture_component_parallel(gbnf_handle h, const float* d_x, int64_t B, int32_t n_comp, const float* d_rho,
+                                    int32_t skip_c, int32_t mix_mode, float* d_G_ll, void* stream);
+
 /* Inverse-CDF resampling, the contract that pins torch.multinomial(w, B, replacement=True)
  * (density_experiment.py:643): idx[i] = #{k : cum_k < u_i}, cum = cumsum_fp64(w) / sum_fp64(w).
  * d_u: float64 uniforms [n] (device). */

@@ -30,9 +30,11 @@ def main():
     B = 128 * 3 * world + 7 * world          # equal shards, ragged tiles
     x_np = np.random.default_rng(99).standard_normal((B, 21)).astype(np.float32)
     x = torch.from_numpy(x_np).to(dev)
-    for mode in ("fp32", "f16fast"):
+    for mode, peer in (("fp32", False), ("fp32", True), ("f16fast", True), ("f16fast", False)):
         model = build_model(md, dev, gemm_mode=mode)
-        ops = gd.KernelOps(model)
+        ops = gd.KernelOps(model, peer=peer)
+        if peer:     # the library-owned peer-memory exchange (gbnf_comm_*): no NCCL call on the data path
+            gd.init_peer_exchange(model, B)
         # single-GPU result (every rank computes it: replicated parameters)
         G = model.mixture_log_density(x, C)
         w = model.boosting_weights(G)
@@ -58,10 +60,22 @@ def main():
         G_cp = gd.mixture_component_parallel(ops, x, C)
         e = rel_err(G_cp.cpu().numpy(), G.cpu().numpy())
         assert e < 2e-6, (mode, e)
+        if peer:     # several epochs back to back (double-buffered slots), then a different batch size
+            for it in range(5):
+                w2 = gd.boosting_weights_batch_parallel(ops, G_loc, "density")
+                assert torch.equal(w2, w_loc), "peer exchange must be deterministic across epochs"
+                G2 = gd.mixture_component_parallel(ops, x, C)
+                assert torch.equal(G2, G_cp)
+            w3 = gd.boosting_weights_batch_parallel(ops, G_loc[:100].contiguous(), "toy", batch_size=100 * world)
+            assert abs(float(w3.double().sum()) * 1.0 - 0.0) >= 0.0
+            tot = w3.double().sum().reshape(1)
+            dist.all_reduce(tot)
+            assert abs(float(tot) - 1.0) < 1e-5
+            gd.shutdown_peer_exchange(model)
         torch.cuda.synchronize()
         model.release()
         if rank == 0:
-            print(f"[{mode}] world {world}: batch-parallel weights / resampling and component-parallel mixture match (G cp rel {e:.1e})")
+            print(f"[{mode}{' peer-memory exchange' if peer else ' torch.distributed collectives'}] world {world}: batch-parallel weights / resampling and component-parallel mixture match (G cp rel {e:.1e})")
     dist.barrier()
     if rank == 0:
         print("MULTI-GPU CHECK OK")
