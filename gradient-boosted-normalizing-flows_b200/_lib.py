@@ -36,6 +36,11 @@ class StepParams(C.Structure):
                 ("W", (C.c_void_p * GBNF_MAX_LAYERS) * 2), ("b", (C.c_void_p * GBNF_MAX_LAYERS) * 2)]
 
 
+class StepGrads(C.Structure):
+    _fields_ = [("an_bias", C.c_void_p), ("an_logs", C.c_void_p),
+                ("W", (C.c_void_p * GBNF_MAX_LAYERS) * 2), ("b", (C.c_void_p * GBNF_MAX_LAYERS) * 2)]
+
+
 class ComponentParams(C.Structure):
     _fields_ = [("flip_init", C.c_int32), ("n_steps", C.c_int32), ("steps", C.POINTER(StepParams))]
 
@@ -63,6 +68,7 @@ SIGNATURES = {
     "gbnf_weight_stats": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "gbnf_weight_apply": (C.c_int, [_vp, _vp, _i64, _vp, _f32, _f32, _i32, _vp, _vp, _vp]),
     "gbnf_weight_renorm": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),
+    "gbnf_component_backward": (C.c_int, [_vp, _i32, C.POINTER(ComponentParams), _vp, _i64, _vp, _vp, C.POINTER(StepGrads), _vp, _vp]),
     "gbnf_comm_local_handle": (C.c_int, [_vp, _i64, _vp]),
     "gbnf_comm_init": (C.c_int, [_vp, _i32, _i32, _vp]),
     "gbnf_comm_destroy": (C.c_int, [_vp]),

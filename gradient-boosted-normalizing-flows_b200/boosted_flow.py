@@ -32,6 +32,28 @@ def _f32c(t):
     return t
 
 
+class _FusedComponentFlow(torch.autograd.Function):
+    """(z, log_det_j) = flows[c](x) for the component that is being TRAINED, both directions served by the library: the forward
+    is the fixed-component kernel (nothing saved), the backward recomputes in-kernel and returns the gradients of every
+    parameter of the component (gbnf_component_backward).  density_experiment.py:647-661 + loss.backward() :361."""
+
+    @staticmethod
+    def forward(ctx, model, c, x, *params):
+        with torch.no_grad():
+            z, ldj = model.component_forward(x, c)
+        ctx.model, ctx.c, ctx.params = model, c, params
+        ctx.save_for_backward(x)
+        return z, ldj
+
+    @staticmethod
+    def backward(ctx, dz, dldj):
+        (x,) = ctx.saved_tensors
+        dz = torch.zeros_like(x) if dz is None else dz.contiguous().float()
+        dldj = torch.zeros(x.shape[0], device=x.device) if dldj is None else dldj.contiguous().float()
+        grads = ctx.model._component_backward(ctx.c, x, dz, dldj)
+        return (None, None, None) + tuple(grads[id(p)] if p.requires_grad else None for p in ctx.params)
+
+
 class BoostedFlow(nn.Module):
     def __init__(self, args, gemm_mode=None):
         super().__init__()
@@ -59,6 +81,7 @@ class BoostedFlow(nn.Module):
         # ---- kernel-side state (created lazily on first use on a CUDA device) ----
         self.gemm_mode = gemm_mode or getattr(args, "gemm_mode", "f16")
         self.toy_base = bool(getattr(args, "toy_base", False))   # toy_experiment.py uses model.base_dist
+        self.fused_backward = bool(getattr(args, "fused_backward", True))   # train the new component through the library
         self._handle = None
         self._handle_device = None
         self._handle_cfg = None
@@ -110,15 +133,61 @@ class BoostedFlow(nn.Module):
         c = self._sample_component(components) if isinstance(components, str) else components
         flow = self.flows[c]
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in flow.parameters())
-        if needs_grad or not flow.actnorm_ready():
-            # component under training (autograd) or first-batch ActNorm initialisation: caller-side torch code
-            z, ldj = flow.forward_autograd(x)
+        if not flow.actnorm_ready():
+            z, ldj = flow.forward_autograd(x)     # first training batch: data-dependent ActNorm initialisation (layers.py:473-486)
+        elif needs_grad and self._fused_backward_ok(x):
+            # component under training: forward AND backward through the library (recompute-in-kernel backward)
+            z, ldj = _FusedComponentFlow.apply(self, c, x.detach().contiguous(), *list(flow.parameters()))
+        elif needs_grad:
+            z, ldj = flow.forward_autograd(x)     # configurations the fused backward does not cover: the caller's autograd
         else:
             z, ldj = self.component_forward(x, c)
         zeros = x.new_zeros((x.shape[0], self.z_size))
         return z, zeros, zeros.clone(), ldj, None
 
     @torch.no_grad()
+    def _fused_backward_ok(self, x):
+        a = self.args
+        return (self.fused_backward and x.is_cuda and x.dtype == torch.float32 and self.component_type == "glow"
+                and a.coupling_network_depth == 1 and a.h_size <= 512 and self.z_size <= 64 and a.num_flows <= 32
+                and a.coupling_network in ("tanh", "relu"))
+
+    def _component_backward(self, c, x, dz, dldj):
+        """Gradients of component c's parameters for upstream (dz, dldj): {id(param): grad} (gbnf_component_backward)."""
+        lib = _lib.load()
+        device = x.device
+        h = self.handle(device)
+        steps = self._component_tensors(c)
+        parr = (_lib.StepParams * len(steps))()
+        garr = (_lib.StepGrads * len(steps))()
+        keep, out = [], {}
+
+        def dev(t, dtype=torch.float32):
+            t = t.detach().to(device=device, dtype=dtype).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def grad_of(pm):
+            g = torch.empty_like(pm, dtype=torch.float32, device=device).contiguous()
+            out[id(pm)] = g
+            return g.data_ptr()
+
+        for k, (d, step) in enumerate(zip(steps, self.flows[c].steps())):
+            sp, sg = parr[k], garr[k]
+            sp.an_bias, sp.an_logs = dev(d["an_bias"].reshape(-1)), dev(d["an_logs"].reshape(-1))
+            sp.perm = dev(d["perm"], torch.int64)
+            sg.an_bias, sg.an_logs = grad_of(step.actnorm.bias), grad_of(step.actnorm.logs)
+            for l, lin in enumerate(d["nets"][0]):
+                sp.W[0][l], sp.b[0][l] = dev(lin.weight), dev(lin.bias)
+                sg.W[0][l], sg.b[0][l] = grad_of(lin.weight), grad_of(lin.bias)
+        cp = _lib.ComponentParams()
+        cp.flip_init, cp.n_steps = 0, len(steps)
+        cp.steps = C.cast(parr, C.POINTER(_lib.StepParams))
+        _lib.check(lib.gbnf_component_backward(h, c, C.byref(cp), _ptr(x), x.shape[0], _ptr(dz), _ptr(dldj),
+                                               C.cast(garr, C.POINTER(_lib.StepGrads)), None, _stream(device)))
+        self._keepalive[("bwd", c)] = keep
+        return out
+
     def decode(self, z, y_onehot, temperature, components):
         """x = flows[c]^{-1}(z) for ONE component c (models/boosted_flow.py:209-218; upstream's `y_onhot` keyword typo is not
         reproduced).  z = None draws sample_size rows from the prior N(0, (exp(0) * temperature)^2) as Glow.decode /

@@ -16,6 +16,7 @@
 #include "coupling_tc.cuh"
 #include "coupling_tc2.cuh"
 #include "coupling_tc3.cuh"
+#include "train_bwd.cuh"
 
 using namespace gbnf;
 
@@ -102,6 +103,17 @@ struct gbnf_ctx {
   CommView cv{};
   float* cp_tmp = nullptr;       // component-parallel fallback: local log q block before the scatter kernel
   long long cp_tmp_cap = 0;
+  // backward of the component under training (gbnf_component_backward)
+  float* tr_w = nullptr;         // fp32 copies of its weights in both layouts + padded biases + 1024 zeros
+  long long tr_w_floats = 0;
+  float* tr_scratch = nullptr;   // per-step activations / d pre-activations [B][...]
+  long long tr_rows = 0;
+  TrainStep* tr_steps_d = nullptr;
+  TrainPackJob* tr_pack_d = nullptr;
+  WgradJob* tr_jobs_d = nullptr;
+  std::vector<TrainStep> tr_steps_h;
+  std::vector<TrainPackJob> tr_pack_h;
+  std::vector<WgradJob> tr_jobs_h;
 };
 constexpr size_t kCommBlockBytes = 4096;
 static_assert(sizeof(CommBlock) <= kCommBlockBytes, "CommBlock does not fit its slot");
@@ -441,6 +453,7 @@ void gbnf_destroy(gbnf_handle h) {
   cudaFree(h->steps_d); cudaFree(h->comps_d); cudaFree(h->fblob); cudaFree(h->iblob); cudaFree(h->wblob);
   cudaFree(h->step_params_d); cudaFree(h->partial); cudaFree(h->ticket); cudaFree(h->ms); cudaFree(h->wsum);
   cudaFree(h->lse_part); cudaFree(h->tile_ctr);
+  cudaFree(h->tr_w); cudaFree(h->tr_scratch); cudaFree(h->tr_steps_d); cudaFree(h->tr_pack_d); cudaFree(h->tr_jobs_d);
   cudaFree(h->cum); cudaFree(h->tile_sums); cudaFree(h->tile_offs); cudaFree(h->prof);
   delete h;
 }
@@ -659,6 +672,101 @@ int gbnf_boost_weights(gbnf_handle h, const float* d_G_ll, int64_t B, float clam
   weight_apply_kernel<<<g, kMixThreads, 0, st>>>(d_G_ll, B, h->ms, clamp_lo, clamp_hi, d_w, h->wsum, d_stats, CommView{}, h->ticket + 1, h->flags);
   weight_renorm_kernel<<<g, kMixThreads, 0, st>>>(d_w, B, h->wsum, mode == GBNF_WEIGHTS_TOY ? 1 : 0, d_stats, CommView{}, h->flags);
   h->launches += 4;
+  CUDA_TRY_H(h, cudaGetLastError());
+  return GBNF_OK;
+}
+
+// ---- training: gradients of the component that is being trained ------------------------------------------------------------------
+int gbnf_component_backward(gbnf_handle h, int32_t c, const gbnf_component_params* p, const float* d_x, int64_t B, const float* d_dz,
+                            const float* d_dldj, const gbnf_step_grads* grads, float* d_dx_opt, void* stream) {
+  if (!h || !p || !p->steps || !grads || !d_x || !d_dz || !d_dldj) return fail(GBNF_ERR_INVALID, "null argument");
+  if (c < 0 || c >= h->cfg.C || p->n_steps != h->cfg.K) return fail(GBNF_ERR_INVALID, "bad component index / n_steps");
+  const gbnf_config& cf = h->cfg;
+  if (cf.kind != GBNF_KIND_GLOW || cf.depth != 1 || cf.act == GBNF_ACT_MIXED || cf.h > 512 || cf.D > 64 || cf.K > kTrMaxK)
+    return fail(GBNF_ERR_INVALID, "fused backward: Glow components with coupling_network_depth 1, h <= 512, D <= 64 (others train through "
+                                  "the caller's autograd)");
+  if (B <= 0) return fail(GBNF_ERR_INVALID, "empty batch");
+  ENTER(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = cf.K, D = cf.D, h0 = D / 2, h1 = D - h0;
+  const int n3 = (cf.coupling == GBNF_COUPLING_AFFINE) ? 2 * h1 : h1;
+  const int hp = round_up(cf.h, 64);
+  const int Kd[3] = {h0, cf.h, cf.h}, Nn[3] = {cf.h, cf.h, n3};
+  int Kp[3], Np[3], NKp[3], KNp[3];
+  long long per_step = 0;
+  for (int l = 0; l < 3; ++l) {
+    Kp[l] = round_up(Kd[l], kF32KT); Np[l] = round_up(Nn[l], kF32NT);
+    NKp[l] = round_up(Nn[l], kF32KT); KNp[l] = round_up(Kd[l], kF32NT);
+    per_step += (long long)Kp[l] * Np[l] + (long long)NKp[l] * KNp[l] + Np[l];
+  }
+  const long long need_w = per_step * K + 1024;
+  if (need_w > h->tr_w_floats) {
+    if (h->tr_w) cudaFree(h->tr_w);
+    h->tr_w = nullptr; h->tr_w_floats = 0;
+    CUDA_TRY_H(h, cudaMalloc(&h->tr_w, need_w * sizeof(float)));
+    h->tr_w_floats = need_w;
+  }
+  const int ldz1 = Kp[0];
+  const long long per_row = (long long)ldz1 + 4LL * hp + 64;
+  if (B > h->tr_rows) {
+    if (h->tr_scratch) cudaFree(h->tr_scratch);
+    h->tr_scratch = nullptr; h->tr_rows = 0;
+    const long long rows = std::max<long long>(B, 1024);
+    CUDA_TRY_H(h, cudaMalloc(&h->tr_scratch, (size_t)rows * per_row * K * sizeof(float)));
+    h->tr_rows = rows;
+  }
+  if (!h->tr_steps_d) {
+    CUDA_TRY_H(h, cudaMalloc(&h->tr_steps_d, (size_t)K * sizeof(TrainStep)));
+    CUDA_TRY_H(h, cudaMalloc(&h->tr_pack_d, (size_t)K * 3 * sizeof(TrainPackJob)));
+    CUDA_TRY_H(h, cudaMalloc(&h->tr_jobs_d, (size_t)K * 3 * sizeof(WgradJob)));
+  }
+  h->tr_steps_h.assign(K, TrainStep{}); h->tr_pack_h.assign((size_t)K * 3, TrainPackJob{}); h->tr_jobs_h.assign((size_t)K * 3, WgradJob{});
+  float* zeros = h->tr_w + per_step * K;
+  int tile0 = 0;
+  for (int k = 0; k < K; ++k) {
+    const gbnf_step_params& sp = p->steps[k];
+    const gbnf_step_grads& sg = grads[k];
+    if (!sp.an_bias || !sp.an_logs || !sp.perm || !sg.an_bias || !sg.an_logs) return fail(GBNF_ERR_INVALID, "glow step needs ActNorm / perm / gradient pointers");
+    TrainStep& ts = h->tr_steps_h[k];
+    ts.an_bias = sp.an_bias; ts.an_logs = sp.an_logs; ts.perm = (const long long*)sp.perm;
+    ts.g_bias = sg.an_bias; ts.g_logs = sg.an_logs;
+    float* w = h->tr_w + per_step * k;
+    float* sc = h->tr_scratch + (size_t)k * h->tr_rows * per_row;
+    ts.z1 = sc; ts.h1 = ts.z1 + h->tr_rows * ldz1; ts.h2 = ts.h1 + h->tr_rows * hp; ts.d1 = ts.h2 + h->tr_rows * hp;
+    ts.d2 = ts.d1 + h->tr_rows * hp; ts.d3 = ts.d2 + h->tr_rows * hp;
+    for (int l = 0; l < 3; ++l) {
+      if (!sp.W[0][l] || !sp.b[0][l] || !sg.W[0][l] || !sg.b[0][l]) return fail(GBNF_ERR_INVALID, "missing Linear weight / bias / gradient pointer");
+      TrainPackJob& pj = h->tr_pack_h[(size_t)k * 3 + l];
+      pj.W = sp.W[0][l]; pj.b = sp.b[0][l]; pj.N = Nn[l]; pj.Kd = Kd[l]; pj.Kp = Kp[l]; pj.Np = Np[l]; pj.NKp = NKp[l]; pj.KNp = KNp[l];
+      pj.Wt = w; w += (long long)Kp[l] * Np[l];
+      pj.Wn = w; w += (long long)NKp[l] * KNp[l];
+      pj.bp = w; w += Np[l];
+      ts.Wt[l] = pj.Wt; ts.Wn[l] = pj.Wn; ts.b[l] = pj.bp; ts.Kp[l] = Kp[l]; ts.Np[l] = Np[l]; ts.NKp[l] = NKp[l]; ts.KNp[l] = KNp[l];
+      WgradJob& wj = h->tr_jobs_h[(size_t)k * 3 + l];
+      wj.dact = (l == 0) ? ts.d1 : (l == 1) ? ts.d2 : ts.d3;  wj.ld_d = (l == 2) ? 64 : hp;
+      wj.in = (l == 0) ? ts.z1 : (l == 1) ? ts.h1 : ts.h2;     wj.ld_i = (l == 0) ? ldz1 : hp;
+      wj.dW = sg.W[0][l]; wj.db = sg.b[0][l]; wj.N = Nn[l]; wj.Kd = Kd[l];
+      wj.tiles_n = (Nn[l] + 63) / 64; wj.tiles_k = (Kd[l] + 63) / 64; wj.tile0 = tile0;
+      tile0 += wj.tiles_n * wj.tiles_k;
+    }
+    CUDA_TRY_H(h, cudaMemsetAsync(sg.an_bias, 0, (size_t)D * sizeof(float), st));
+    CUDA_TRY_H(h, cudaMemsetAsync(sg.an_logs, 0, (size_t)D * sizeof(float), st));
+  }
+  CUDA_TRY_H(h, cudaMemcpyAsync(h->tr_steps_d, h->tr_steps_h.data(), (size_t)K * sizeof(TrainStep), cudaMemcpyHostToDevice, st));
+  CUDA_TRY_H(h, cudaMemcpyAsync(h->tr_pack_d, h->tr_pack_h.data(), (size_t)K * 3 * sizeof(TrainPackJob), cudaMemcpyHostToDevice, st));
+  CUDA_TRY_H(h, cudaMemcpyAsync(h->tr_jobs_d, h->tr_jobs_h.data(), (size_t)K * 3 * sizeof(WgradJob), cudaMemcpyHostToDevice, st));
+  CUDA_TRY_H(h, cudaMemsetAsync(zeros, 0, 1024 * sizeof(float), st));
+  train_pack_kernel<<<dim3(32, K * 3), 256, 0, st>>>(h->tr_pack_d);
+  TrainArgs ta{};
+  ta.x = d_x; ta.B = B; ta.dz = d_dz; ta.dldj = d_dldj; ta.steps = h->tr_steps_d; ta.K = K; ta.D = D; ta.h = cf.h; ta.hp = hp;
+  ta.act = cf.act; ta.coupling = cf.coupling; ta.in_dim = h0; ta.out_dim = h1; ta.n3 = n3; ta.ld = hp + 4; ta.zeros = zeros; ta.dx = d_dx_opt;
+  const size_t smem = ((size_t)(((K + 1) * kTrR * D + 3) & ~3) + (size_t)K * kTrR * 64 + 3ull * kTrR * ta.ld + 2ull * kF32KT * kF32NT +
+                       2ull * ((kTrR * D + 3) & ~3)) * sizeof(float);
+  if (smem > 227 * 1024) return fail(GBNF_ERR_INVALID, "fused backward: shared-memory history too large (K x D)");
+  CUDA_TRY_H(h, cudaFuncSetAttribute(train_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  train_bwd_rows_kernel<<<(unsigned)((B + kTrR - 1) / kTrR), kF32Threads, smem, st>>>(ta);
+  train_wgrad_kernel<<<tile0, 256, 0, st>>>(h->tr_jobs_d, K * 3, B);
+  h->launches += 3;
   CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;
 }

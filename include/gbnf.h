@@ -173,6 +173,24 @@ int gbnf_weight_apply(gbnf_handle h, const float* d_G_ll, int64_t B, const float
                       float clamp_hi, int32_t mode, float* d_w, double* d_wsum, void* stream);
 int gbnf_weight_renorm(gbnf_handle h, float* d_w, int64_t B, const double* d_wsum, int32_t mode, void* stream);
 
+/* ---- training step of the NEW component (density_experiment.py:647-661, 361-374) ------------------------------
+ * Gradients of any loss L(z, log_det_j) of component c's flow with respect to all of its parameters, given the upstream
+ * gradients dL/dz [B, D] and dL/dlog_det_j [B] (for the boosted objective nll = mean(-(log N(z) + ldj)): dz = z / B,
+ * dldj = -1 / B).  Recompute-in-kernel: the forward value comes from gbnf_component_logq and saves nothing; this call
+ * recomputes the activations (fp32 CUDA-core arithmetic, reference-class numerics) and runs the backward sweep.
+ * `p` holds the component's CURRENT raw parameters (as for gbnf_pack_component), `grads` the same tensors' gradient
+ * buffers, which are OVERWRITTEN.  Glow components, coupling_network_depth 1, h <= 512, D <= 64; other configurations
+ * return GBNF_ERR_INVALID and train through the caller's autograd.  d_dx_opt [B, D] (may be NULL) receives dL/dx. */
+typedef struct {
+  float* an_bias;
+  float* an_logs;
+  float* W[2][GBNF_MAX_LAYERS];
+  float* b[2][GBNF_MAX_LAYERS];
+} gbnf_step_grads;
+int gbnf_component_backward(gbnf_handle h, int32_t c, const gbnf_component_params* p, const float* d_x, int64_t B,
+                            const float* d_dz, const float* d_dldj, const gbnf_step_grads* grads, float* d_dx_opt,
+                            void* stream);
+
 /* ---- multi-GPU on one node: one process per GPU, values exchanged through PEER MEMORY over NVLink ------------
  * The reference has no distributed code; this is the library-owned collective SURVEY 8(b) lists as
  * gbnf_comm_init.  No NCCL call sits on the data path: a rank publishes a value by storing it into every rank's

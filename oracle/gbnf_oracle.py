@@ -395,6 +395,30 @@ def evaluate(model, batches, component, all_trained):
 # --------------------------------------------------------------------------------------
 # ActNorm data-dependent init (models/layers.py:473-486) -- used to build synthetic models
 # --------------------------------------------------------------------------------------
+def update_rho(model, batches, component, rho_iters, rho_lr):
+    """Decayed-step SGD on rho[component]: models/boosted_flow.py:141-207 (approximate=True branch).  Per mini-batch:
+    new / fixed / full log-likelihoods with the RAW-rho recursion of _rho_gradients (:119-139), gradient =
+    mean((-g_ll) - (-G_ll)) with g_ll = new, G_ll = fixed (:183-184), step = lr / (0.05 i + 1), rho clamped to [0.01, 100]
+    (:193-194), stop when i > 10 and (i > iters or |delta| < 0.001) (:203-204).  Returns the updated rho vector."""
+    rho = np.array(model["rho"], dtype=np.float32).copy()
+    prev = float(rho[component])
+    n = component + 1
+    for i in range(rho_iters):
+        x = batches[i % len(batches)]
+        m = dict(model); m["rho"] = rho
+        lq = all_component_logq(m, x, n)
+        fixed = mixture_recursion(lq, rho, n - 1, normalized=False) if n > 1 else np.zeros(x.shape[0], dtype=x.dtype)
+        new = lq[:, n - 1] if n > 1 else np.zeros(x.shape[0], dtype=x.dtype)
+        gradient = float(np.mean((-new) - (-fixed)))
+        step = rho_lr / (0.05 * i + 1)
+        r = min(max(prev - step * gradient, 0.01), 100.0)
+        rho[component] = r
+        dif, prev = abs(prev - r), r
+        if i > 10 and (i > rho_iters or dif < 0.001):
+            break
+    return rho
+
+
 def actnorm_init(sample, scale=1.0):
     bias = -np.mean(sample, axis=0)
     var = np.mean((sample + bias) ** 2, axis=0)

@@ -191,6 +191,21 @@ def build_case(name):
                 ev = ref_density.evaluate(model, loader, args)
             for k, v in ev.items():
                 out[f"eval.c{comp}.a{int(all_tr)}.{k}"] = np.array(v)
+        # update_rho loop (models/boosted_flow.py:141-207).  Upstream formats two undefined names into a LOG message at :185
+        # (NameError whenever rho_iters > 0 and component > 0); they are defined here, in the fixture script only, so that the
+        # reference's own loop runs: the arithmetic (decayed-step SGD on rho[component], clamp to [0.01, 100]) is untouched.
+        import models.boosted_flow as ref_bf_module
+        ref_bf_module.g_nll = torch.zeros(2); ref_bf_module.G_nll = torch.zeros(2)
+        rho0 = model.rho.clone()
+        model.component, model.all_trained = C - 1, False
+        args.rho_iters, args.rho_lr, args.snap_dir = 14, 0.05, "/tmp"
+        model.args.rho_iters, model.args.rho_lr, model.args.snap_dir = 14, 0.05, "/tmp"
+        model.update_rho([(x[:B // 2], None), (x[B // 2:], None)])
+        out["urho.rho_final"] = model.rho.detach().numpy().copy()
+        out["urho.iters"] = np.array(14); out["urho.lr"] = np.array(0.05)
+        with torch.no_grad():
+            model.rho.copy_(rho0)
+        model.args.rho_iters = args.rho_iters = 0
         # _rho_gradients raw-rho recursion (models/boosted_flow.py:119-139)
         model.component, model.all_trained = C - 1, False
         new_ll, fixed_ll, full_ll = model._rho_gradients(x)

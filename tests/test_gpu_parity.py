@@ -157,6 +157,23 @@ def test_evaluate_and_rho_gradients_vs_golden(golden, models, name, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["glow_d43", "realnvp_d6_bn"])
+def test_update_rho_loop_vs_golden(golden, name, mode):
+    """BoostedFlow.update_rho (models/boosted_flow.py:141-207) served by the library, against the reference's own loop."""
+    g = golden(name); md = golden_model(g)
+    model = build_model(md, "cuda", gemm_mode=mode, rho_iters=int(g["urho.iters"]), rho_lr=float(g["urho.lr"]))
+    try:
+        x = dev(g["x"]); B = x.shape[0]
+        model.component, model.all_trained = md["C"] - 1, False
+        model.update_rho([(x[:B // 2].contiguous(), None), (x[B // 2:].contiguous(), None)])
+        tol = 1e-4 if mode == "fp32" else 2e-2
+        np.testing.assert_allclose(model.rho.cpu().numpy(), g["urho.rho_final"], rtol=tol, atol=tol * 0.05)
+        assert not np.allclose(model.rho.cpu().numpy(), md["rho"])
+    finally:
+        model.release()
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_toy_objective_vs_golden(golden, models, mode):
     g = golden("toy_d2"); model, md = models("toy_d2", mode)
     x = dev(g["x"])

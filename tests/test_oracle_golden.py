@@ -173,3 +173,14 @@ def test_oracle_component_assignment_matches_sample_component():
     assert all(got[i] == orc.sample_component(rho, 7, float(u[i])) for i in range(500))
     got = orc.assign_components(rho, 7, u, exclude=3)
     assert 3 not in got and all(got[i] == orc.sample_component(rho, 7, float(u[i]), exclude=3) for i in range(500))
+
+
+@pytest.mark.parametrize("name", ["glow_d43", "realnvp_d6_bn"])
+def test_oracle_update_rho_loop_vs_reference(golden, name):
+    """The reference's own update_rho loop (run by make_golden.py with the two undefined log-message names of
+    models/boosted_flow.py:185 defined in the fixture script only)."""
+    g = golden(name); md = golden_model(g)
+    B = g["x"].shape[0]
+    rho = orc.update_rho(md, [g["x"][:B // 2], g["x"][B // 2:]], md["C"] - 1, int(g["urho.iters"]), float(g["urho.lr"]))
+    np.testing.assert_allclose(rho, g["urho.rho_final"], rtol=2e-5, atol=2e-6)
+    assert not np.allclose(rho, md["rho"])
