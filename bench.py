@@ -492,7 +492,7 @@ def run_ours(a):
                    "l2": f"resident rows {a.rows * D * 4 / 1e6:.0f} MB per GPU > 126 MB L2; batches rotate through them",
                    "parallelism": (f"component-parallel x{world} ({C // world} of {C} components per GPU, every GPU sees all "
                                    f"{a.batch} rows of a step; log q [B, C/G] " + ("stored by the coupling epilogue into every rank's gather buffer over NVLink peer memory" if peer else "all-gathered with NCCL") + ")" if comp_par else
-                                   f"batch-parallel x{world} (weak: {a.batch} rows per GPU per step; global softmax via " + ("the library's peer-memory exchange" if peer else "three NCCL scalar all-reduces") + ")")},
+                                   f"batch-parallel x{world} (weak: {a.batch} rows per GPU per step" + ("" if world == 1 else "; global softmax via " + ("the library's peer-memory exchange" if peer else "three NCCL scalar all-reduces")) + ")")},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "coupling (C/G components) + all-gather + mixture" if comp_par else "fused coupling+mixture", "kernel_ms": k_ms, "weights_ms": w_ms,
                      "flops_per_sample": flops_per_sample(cfg),

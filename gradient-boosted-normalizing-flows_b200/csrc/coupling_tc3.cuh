@@ -16,9 +16,11 @@
 //   its partial last-layer product.  The two partial last-layer products (128 x <= 64 fp32) are exchanged the same way, both
 //   CTAs apply the (identical) coupling transform to their own copy of the resident z tile, rank 0 writes the results.
 //
-//   TMEM (512 columns per CTA):  A1_p [0, 256) | slot A [256, 384): own layer-2 chunk (128 fp32 columns, packed in place) |
-//   slot B [384, 448): shipped half chunk (64 columns) | last-layer accumulator [448, 512).  Layer-1 accumulators use slots
-//   A / (B + last) before layer 2 starts.
+//   TMEM (512 columns per CTA):  A1_p [0, 256) | slot A [256, 384): own layer-2 chunk (128 fp32 columns; its fp16 pairs are
+//   packed in place into [256, 320), the vacated upper half [320, 384) then receives that piece's last-layer product, which
+//   the epilogue adds into registers) | slots B0 [384, 448) and B1 [448, 512): the two shipped halves of the peer's chunk,
+//   double buffered so that the second half does not wait for the first one's epilogue.  Layer-1 accumulators use slot A and
+//   B0 + B1 before layer 2 starts.
 //   weights: one linear stream per (step, CTA) in the order the MMA warp consumes it, cut into 16 KB ring stages
 //   (pack_weight_tc3_kernel): W1 half | for chunk pair m = 0..3: two shipped halves [32 k-slabs][64 x 16] of chunk
 //   2 m + 1 - p, then the own chunk 2 m + p [32 k-slabs][128 x 16] | last-layer pieces [8 k-slabs][Np3 x 16] per own chunk.
@@ -38,7 +40,7 @@ constexpr uint32_t kT3StageBytes = 16384;    // 4 k-slabs of [128 x 16] or 8 k-s
 constexpr uint32_t kT3XBytes = 65536;        // exchange buffer: 128 rows x 128 columns fp32, written by the peer CTA
 constexpr int kT3BiasFloats = 512 + 512 + 64; // b1 (own half) | b2 (own chunks) | b3
 // TMEM columns
-constexpr uint32_t kT3SlotA = 256, kT3SlotB = 384, kT3AccL3 = 448;
+constexpr uint32_t kT3SlotA = 256, kT3SlotB0 = 384, kT3SlotB1 = 448, kT3L3Tmp = 320;
 
 struct Tc3Misc {
   uint64_t full[kT3MaxStages];
@@ -47,10 +49,11 @@ struct Tc3Misc {
   uint64_t a1r[4];    // epilogue -> MMA : A1 k-quarter q packed, its layer-1 accumulator drained        (16 arrivals)
   uint64_t l1f[4];    // MMA -> epilogue : layer-1 chunk q accumulated                                   (commit)
   uint64_t l2own;     // MMA -> epilogue : own layer-2 chunk accumulated in slot A                       (commit)
-  uint64_t l2ship;    // MMA -> epilogue : shipped half chunk accumulated in slot B                      (commit)
-  uint64_t sbr;       // epilogue -> MMA : slot B read out                                               (16 arrivals)
+  uint64_t l2ship[2]; // MMA -> epilogue : shipped half chunk y accumulated in slot B y                  (commit)
+  uint64_t sbr[2];    // epilogue -> MMA : slot B y read out                                             (16 arrivals)
+  uint64_t l3r;       // epilogue -> MMA : last-layer piece product read out of slot A's upper half      (16 arrivals)
   uint64_t sr;        // epilogue -> MMA : A2 piece packed in slot A                                     (16 arrivals)
-  uint64_t l3f;       // MMA -> epilogue : partial last-layer product complete                           (commit)
+  uint64_t l3f;       // MMA -> epilogue : last-layer product of ONE own chunk's piece complete          (commit)
   uint64_t xfull;     // PEER epilogue -> epilogue : both halves of a chunk's partial sums are in my exchange buffer (armed by me with expect_tx; the peer's two bulk copies complete it)
   uint64_t x3full;    // PEER epilogue -> epilogue : the peer's partial last-layer product is in my exchange buffer (armed by me; one bulk copy of the peer completes it)
   uint64_t xfree;     // PEER epilogue -> epilogue : the peer has consumed what I last wrote into ITS exchange buffer (16 remote arrivals, relaxed)
@@ -168,8 +171,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
     for (int i = 0; i < nst; ++i) { ptx::mbar_init(&misc->full[i], 1); ptx::mbar_init(&misc->empty[i], 1); }
     ptx::mbar_init(&misc->a0r, 16);
     for (int i = 0; i < 4; ++i) { ptx::mbar_init(&misc->a1r[i], 16); ptx::mbar_init(&misc->l1f[i], 1); }
-    ptx::mbar_init(&misc->l2own, 1); ptx::mbar_init(&misc->l2ship, 1);
-    ptx::mbar_init(&misc->sbr, 16); ptx::mbar_init(&misc->sr, 16); ptx::mbar_init(&misc->l3f, 1);
+    ptx::mbar_init(&misc->l2own, 1); ptx::mbar_init(&misc->l2ship[0], 1); ptx::mbar_init(&misc->l2ship[1], 1);
+    ptx::mbar_init(&misc->sbr[0], 16); ptx::mbar_init(&misc->sbr[1], 16); ptx::mbar_init(&misc->sr, 16); ptx::mbar_init(&misc->l3f, 1);
+    ptx::mbar_init(&misc->l3r, 16);
     ptx::mbar_init(&misc->xfull, 1); ptx::mbar_init(&misc->x3full, 1); ptx::mbar_init(&misc->xfree, 16);
     ptx::fence_mbar_init();
     ptx::mbar_arrive_expect_tx(&misc->xfull, kT3XBytes);     // armed for the first chunk the peer ships (two 32 KB bulk copies)
@@ -249,7 +253,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================================
     uint32_t units = 0;
-    uint32_t n_sbr = 0, n_sr = 0;                    // waits done so far on the slot-B / packed-piece barriers
+    uint32_t n_sbr[2] = {0, 0}, n_sr = 0, n_l3r = 0;  // waits done so far on the slot-B / packed-piece / piece-read barriers
     int nslot = 0, slot = 0;
     uint32_t npar = 0;
     const long long m_t0 = T3_CLK();
@@ -302,7 +306,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
             if (q >= 2) wait_epi(&misc->a1r[q - 2], upar, 22);                    // its accumulator slot has been read out
             m_wa += T3_CLK() - tw;
             if (ptx::elect_one()) {
-              const uint32_t d = tbase + ((q & 1) ? kT3SlotB : kT3SlotA);
+              const uint32_t d = tbase + ((q & 1) ? kT3SlotB0 : kT3SlotA);
               // chunk q = k0s k-slabs of [128 x 16] at byte q * k0s * 4096 of the W1 half image (16 KB per held stage)
               const uint32_t byte0 = (uint32_t)(q * k0s) * 4096u;
               const uint64_t bq = l1_desc[byte0 >> 14] + (uint64_t)((byte0 & 16383u) >> 4);
@@ -320,6 +324,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           // ---- layer 2 (partial sums over my K half) and my partial last-layer product ----
           t3_schedule(p, [&](int op, int x, int y) {
             if (op == T3_OP_OWN) {
+              if ((x >> 1) > 0) {                    // the previous piece's last-layer product has been read out of slot A
+                tw = T3_CLK();
+                wait_epi(&misc->l3r, n_l3r & 1u, 26);
+                m_ws += T3_CLK() - tw;
+                ++n_l3r;
+              }
               for (int t = 0; t < 8; ++t) {
                 const uint64_t bd = acquire();
                 const int cur = slot;
@@ -335,19 +345,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
               }
             } else if (op == T3_OP_SHIP) {
               tw = T3_CLK();
-              wait_epi(&misc->sbr, (n_sbr & 1u) ^ 1u, 25);                        // slot B read out (passes the first time)
+              wait_epi(&misc->sbr[y], (n_sbr[y] & 1u) ^ 1u, 25);                  // slot B y read out (passes the first time)
               m_wb += T3_CLK() - tw;
-              ++n_sbr;
+              ++n_sbr[y];
               for (int t = 0; t < 4; ++t) {
                 const uint64_t bd = acquire();
                 const int cur = slot;
                 if (ptx::elect_one()) {
-                  const uint32_t d = tbase + kT3SlotB;
+                  const uint32_t d = tbase + (y ? kT3SlotB1 : kT3SlotB0);
 #pragma unroll
                   for (int i = 0; i < 8; ++i)
                     ptx::umma_f16_ts(d, tbase + 8u * (uint32_t)(8 * t + i), bd + (uint64_t)(i * 128), idesc_64, (t > 0 || i > 0) ? 1u : 0u);
                   ptx::umma_commit(&misc->empty[cur]);
-                  if (t == 3) ptx::umma_commit(&misc->l2ship);
+                  if (t == 3) ptx::umma_commit(&misc->l2ship[y]);
                 }
                 __syncwarp();
               }
@@ -360,11 +370,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
               m_ws += T3_CLK() - tw;
               ++n_sr;
               if (ptx::elect_one()) {
-                const uint32_t at = tbase + kT3SlotA, d = tbase + kT3AccL3;
+                const uint32_t at = tbase + kT3SlotA, d = tbase + kT3L3Tmp;       // fresh product per piece, summed by the epilogue
                 for (int i = 0; i < 8; ++i)
-                  ptx::umma_f16_ts(d, at + 8u * (uint32_t)i, bd + (uint64_t)((uint32_t)i * b3_step), idesc_o, (x > 0 || i > 0) ? 1u : 0u);
+                  ptx::umma_f16_ts(d, at + 8u * (uint32_t)i, bd + (uint64_t)((uint32_t)i * b3_step), idesc_o, i > 0 ? 1u : 0u);
                 ptx::umma_commit(&misc->empty[cur]);
-                if (x == 3) ptx::umma_commit(&misc->l3f);
+                ptx::umma_commit(&misc->l3f);
               }
               __syncwarp();
             }
@@ -386,7 +396,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
     const int dq = (D + 3) >> 2;
     const int h0col = min(D, g * dq), h1col = min(D, (g + 1) * dq);
     uint32_t units = 0;
-    uint32_t n_own = 0, n_ship = 0, n_xfree = 0;     // waits done so far on l2own / xfull, l2ship, xfree
+    uint32_t n_own = 0, n_ship[2] = {0, 0}, n_xfree = 0, n_l3f = 0;   // waits done so far on l2own / xfull, l2ship, xfree, l3f
     const long long e_t0 = T3_CLK();
     long long e_l1f = 0, e_own = 0, e_xfull = 0, e_ship = 0, e_xfree = 0, e_l3f = 0, e_x3 = 0, e_g = 0, e_c1 = 0, e_c2 = 0, e_c3 = 0, e_c4 = 0, tq;
     float* const part = reinterpret_cast<float*>(A0);
@@ -512,7 +522,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
             uint32_t pk[16];
             {
               uint32_t r[32];
-              ptx::tmem_ld32(lane_base + ((q & 1) ? kT3SlotB : kT3SlotA) + (uint32_t)g * 32u, r);
+              ptx::tmem_ld32(lane_base + ((q & 1) ? kT3SlotB0 : kT3SlotA) + (uint32_t)g * 32u, r);
               ptx::tmem_ld_wait();
               if (act_kind == 1) t2_act_pack32<1, TANH_MODE>(r, bias_c + q * 128 + g * 32, pk, a.error_flag);
               else               t2_act_pack32<2, TANH_MODE>(r, bias_c + q * 128 + g * 32, pk, a.error_flag);
@@ -525,10 +535,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           }
           // the next pass's constants (other buffer: its last readers finished a pass ago)
           if (sd_next != nullptr) stage_pass(sd_next, buf ^ 1);
-          // ---- layer 2 in my op order ----
-          t3_schedule(p, [&](int op, int x, int y) {
-            if (op == T3_OP_OWN) {
-              const int m = x >> 1;
+          // ---- layer 2: per chunk pair m -- [read out the previous own chunk's last-layer product] -> the two shipped halves
+          //      (their MMAs ran under the previous own epilogue) -> my own chunk ----
+          const int c0 = g * 16;
+          float acc3[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc3[i] = 0.f;
+          auto l3read = [&](int mm) {
+            tq = T3_CLK();
+            t2_wait(&misc->l3f, n_l3f & 1u, a.error_flag, 32, lane);
+            ++n_l3f;
+            e_l3f += T3_CLK() - tq;
+            ptx::tc_fence_after();
+            if (c0 < np3) {
+              uint32_t r3[16];
+              ptx::tmem_ld16(lane_base + kT3L3Tmp + (uint32_t)c0, r3);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc3[i] += __uint_as_float(r3[i]);
+            }
+            ptx::tc_fence_before();
+            if (mm < 3) t2_warp_arrive(&misc->l3r, lane);      // slot A may take the next own chunk
+          };
+          for (int m = 0; m < 4; ++m) {
+            if (m > 0) l3read(m - 1);
+            for (int y = 0; y < 2; ++y) {
+              tq = T3_CLK();
+              t2_wait(&misc->l2ship[y], n_ship[y] & 1u, a.error_flag, 34, lane);
+              e_ship += T3_CLK() - tq;
+              tq = T3_CLK();
+              ++n_ship[y];
+              ptx::tc_fence_after();
+              uint32_t r[16];
+              ptx::tmem_ld16(lane_base + (y ? kT3SlotB1 : kT3SlotB0) + (uint32_t)g * 16u, r);
+              ptx::tmem_ld_wait();
+              ptx::tc_fence_before();
+              t2_warp_arrive(&misc->sbr[y], lane);   // slot B y may be overwritten by the next pair's half
+              // The half chunk goes to the peer as ONE 32 KB bulk copy out of a local staging buffer (DSMEM stores from 512
+              // threads ran at ~10 B/clk and kept the epilogue warps busy for 3.4 k cycles per half; the copy engine moves
+              // ~20 B/clk on its own).  Staging layout = destination layout: float4 (c4 * 128 + row), c4 = column / 4.
+              if (et == 0) ptx::bulk_wait_read0();   // my previous copy has read the staging buffer
+              t2_epi_bar();
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                stg[(4 * g + i) * kTcRows + row] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+              ptx::fence_proxy_async_smem();
+              t2_epi_bar();
+              if (et == 0) {
+                if (y == 0) {                        // the peer has consumed the previous chunk I wrote into its buffer
+                  const long long tx = T3_CLK();
+                  ptx::mbar_wait_cluster(&misc->xfree, (n_xfree & 1u) ^ 1u, a.error_flag, 35);
+                  e_xfree += T3_CLK() - tx;
+                }
+                ptx::bulk_s2c(xb_peer + (uint32_t)y * (kT3XBytes / 2), stg, kT3XBytes / 2, xfull_peer);
+                ptx::bulk_commit();
+              }
+              if (y == 0) ++n_xfree;
+              e_c3 += T3_CLK() - tq;
+            }
+            {
               tq = T3_CLK();
               t2_wait(&misc->l2own, n_own & 1u, a.error_flag, 31, lane);
               e_own += T3_CLK() - tq;
@@ -556,60 +622,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
                                                                                   // passed: the peer ships only after 16 xfree arrivals)
               remote_arrive(xfree_peer);             // my exchange buffer may be overwritten
               e_c2 += T3_CLK() - tq;
-            } else if (op == T3_OP_SHIP) {
-              tq = T3_CLK();
-              t2_wait(&misc->l2ship, n_ship & 1u, a.error_flag, 34, lane);
-              e_ship += T3_CLK() - tq;
-              tq = T3_CLK();
-              ++n_ship;
-              ptx::tc_fence_after();
-              uint32_t r[16];
-              ptx::tmem_ld16(lane_base + kT3SlotB + (uint32_t)g * 16u, r);
-              ptx::tmem_ld_wait();
-              ptx::tc_fence_before();
-              t2_warp_arrive(&misc->sbr, lane);      // slot B may be overwritten by the next half
-              // The half chunk goes to the peer as ONE 32 KB bulk copy out of a local staging buffer (DSMEM stores from 512
-              // threads ran at ~10 B/clk and kept the epilogue warps busy for 3.4 k cycles per half; the copy engine moves
-              // ~20 B/clk on its own).  Staging layout = destination layout: float4 (c4 * 128 + row), c4 = column / 4.
-              if (et == 0) ptx::bulk_wait_read0();   // my previous copy has read the staging buffer
-              t2_epi_bar();
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                stg[(4 * g + i) * kTcRows + row] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-              ptx::fence_proxy_async_smem();
-              t2_epi_bar();
-              if (et == 0) {
-                if (y == 0) {                        // the peer has consumed the previous chunk I wrote into its buffer
-                  const long long tx = T3_CLK();
-                  ptx::mbar_wait_cluster(&misc->xfree, (n_xfree & 1u) ^ 1u, a.error_flag, 35);
-                  e_xfree += T3_CLK() - tx;
-                }
-                ptx::bulk_s2c(xb_peer + (uint32_t)y * (kT3XBytes / 2), stg, kT3XBytes / 2, xfull_peer);
-                ptx::bulk_commit();
-              }
-              if (y == 0) ++n_xfree;
-              e_c3 += T3_CLK() - tq;
             }
-          });
-          // ---- last layer: exchange the partial products, then the coupling transform on this thread's 16-column slice ----
-          tq = T3_CLK();
-          t2_wait(&misc->l3f, upar, a.error_flag, 32, lane);
-          e_l3f += T3_CLK() - tq;
-          ptx::tc_fence_after();
-          const int c0 = g * 16;
-          uint32_t r[16];
-          if (c0 < np3) {
-            ptx::tmem_ld16(lane_base + kT3AccL3 + (uint32_t)c0, r);
-            ptx::tmem_ld_wait();
           }
+          // ---- last layer: my partial product = the four pieces summed in registers; exchange the partial products, then the
+          //      coupling transform on this thread's 16-column slice ----
+          l3read(3);
           if (et == 0) ptx::bulk_wait_read0();
           t2_epi_bar();
           if (c0 < np3) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              stg[(4 * g + i) * kTcRows + row] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                             __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+              stg[(4 * g + i) * kTcRows + row] = make_float4(acc3[4 * i], acc3[4 * i + 1], acc3[4 * i + 2], acc3[4 * i + 3]);
           }
           ptx::fence_proxy_async_smem();
           t2_epi_bar();
@@ -631,10 +654,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 o = xb[(4 * g + i) * kTcRows + row];
-              acc[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + o.x;      // a + b == b + a: both CTAs get the same bits
-              acc[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + o.y;
-              acc[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + o.z;
-              acc[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + o.w;
+              acc[4 * i + 0] = acc3[4 * i + 0] + o.x;      // a + b == b + a: both CTAs get the same bits
+              acc[4 * i + 1] = acc3[4 * i + 1] + o.y;
+              acc[4 * i + 2] = acc3[4 * i + 2] + o.z;
+              acc[4 * i + 3] = acc3[4 * i + 3] + o.w;
             }
             const float* bias = bias_c + 1024;
             if (md.coupling == GBNF_COUPLING_AFFINE) {
