@@ -48,7 +48,7 @@ class ComponentParams(C.Structure):
 class Info(C.Structure):
     _fields_ = [("gemm_mode", C.c_int32), ("rows_per_cta", C.c_int32), ("smem_bytes", C.c_int32), ("tmem_cols", C.c_int32),
                 ("num_sms", C.c_int32), ("grid", C.c_int32), ("packed_bytes", C.c_int64), ("launches", C.c_int64),
-                ("pipelined", C.c_int32), ("reserved", C.c_int32)]
+                ("pipelined", C.c_int32), ("two_chain", C.c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/gbnf.h one to one (tests/test_abi.py checks the two stay in sync)

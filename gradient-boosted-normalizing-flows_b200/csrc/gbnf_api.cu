@@ -16,6 +16,7 @@
 #include "coupling_tc.cuh"
 #include "coupling_tc2.cuh"
 #include "coupling_tc3.cuh"
+#include "coupling_tc4.cuh"
 #include "train_bwd.cuh"
 
 using namespace gbnf;
@@ -91,6 +92,10 @@ struct gbnf_ctx {
   TcPlan tc{};
   bool tc2 = false;              // pipelined tensor-core kernel (coupling_tc2.cuh) selected
   bool tc3 = false;              // CTA-pair tensor-core kernel for h = 1024 (coupling_tc3.cuh) selected
+  bool tc4 = false;              // two-chain kernel (coupling_tc4.cuh) available for this shape: Glow / affine / tanh, h = 512
+  TcPlan tc4plan{};
+  int last_two_chain = 0;        // the most recent coupling launch went through coupling_tc4_kernel
+  bool tc4_force = false;        // GBNF_TC4=2
   int tc3_pairs = 0;             // CTA pairs the device keeps resident at once (cudaOccupancyMaxActiveClusters)
   int profiling = 0;             // GBNF_PROF=1: cycle counters + event trace, 2: event trace only (gbnf_get_profile / _trace)
   int last_grid = 0;
@@ -146,7 +151,7 @@ int check_status(gbnf_ctx* h) {
     return fail(GBNF_ERR_CUDA, "kernel watchdog: a bounded wait timed out (code " + std::to_string(code) + ": " + watchdog_text(code) +
                                    "); the kernel trapped and the CUDA context is unusable");
   }
-  if (f[2] != 0) {
+  if (f[2] != 0 && std::getenv("GBNF_EXP") == nullptr) {     // (GBNF_EXP: timing experiments compute garbage on purpose)
     f[2] = 0;
     return fail(GBNF_ERR_NUMERIC, "an input or activation of an earlier launch was not finite in fp16 (|v| > 65504, inf or NaN): its "
                                   "results are invalid; standardise the data or use GBNF_GEMM_FP32");
@@ -250,10 +255,15 @@ int plan_layout(gbnf_ctx* h) {
           sd.layer[net][0].NC = kT2Chunk;
           sd.layer[net][1].NC = kT2Chunk; sd.layer[net][1].NC2 = (md.h == 512) ? kT2Piece : 0;
         }
+      // two-chain schedule on the same packed image (GBNF_TC4=0 keeps the single-chain kernel, for A/B measurements)
+      const char* no_tc4 = std::getenv("GBNF_TC4");
+      h->tc4 = tc4_eligible(md, h->steps_h) && !(no_tc4 && no_tc4[0] == '0') && tc4_make_plan(md, h->steps_h, &h->tc4plan);
+      h->tc4_force = h->tc4 && no_tc4 && no_tc4[0] == '2';
     } else if (!tc_make_plan(md, h->steps_h, &h->tc, &why)) {
       return fail(GBNF_ERR_INVALID, "f16 tensor-core path: " + why);
     }
     h->tc.tanh_mode = (c.gemm_mode == GBNF_GEMM_F16_TC_FAST) ? 0 : 1;
+    h->tc4plan.tanh_mode = h->tc.tanh_mode;
     { const char* pe = std::getenv("GBNF_PROF"); h->profiling = (pe && pe[0] >= '1' && pe[0] <= '2') ? pe[0] - '0' : 0; }
     h->rows_per_cta = 128;
     h->smem_bytes = h->tc.smem_bytes;
@@ -315,16 +325,25 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
   a.num_tiles = (int)((B + R - 1) / R);
   a.split = 1; a.comps_per_unit = c1 - c0; a.num_units = a.num_tiles;
   const int workers = h->tc3 ? h->tc3_pairs : h->num_sms;        // CTAs, or CTA pairs, that run concurrently
+  bool two_chain = false;
   if (h->cfg.gemm_mode != GBNF_GEMM_FP32 && (h->tc2 || h->tc3)) {
     // split every tile's components over S units when that shortens the critical CTA (waves x components per unit)
     const int ncomp = c1 - c0;
     long long best = -1;
+    // The two-chain kernel pairs the two halves of a unit's components: every unit needs the same, even number of them.  A pass
+    // of it takes ~0.8 of a single-chain pass, which the cost model weighs against the coarser units (GBNF_TC4=2: always
+    // prefer it when a split allows it -- tests).
+    const bool tc4_ok = h->tc4 && h->profiling != 2 && z_out == nullptr;
+    bool best_two = false;
     for (int S = 1; S <= ncomp; S *= 2) {
       const int cpu = (ncomp + S - 1) / S;
       const int units = a.num_tiles * ((ncomp + cpu - 1) / cpu);
-      const long long cost = (long long)((units + workers - 1) / workers) * cpu;
-      if (best < 0 || cost < best) { best = cost; a.comps_per_unit = cpu; a.split = (ncomp + cpu - 1) / cpu; }
+      const bool two = tc4_ok && cpu % 2 == 0 && ncomp % cpu == 0;
+      long long cost = (long long)((units + workers - 1) / workers) * cpu * (two ? 4 : 5);
+      if (h->tc4_force && !two) cost += 1LL << 40;
+      if (best < 0 || cost < best) { best = cost; a.comps_per_unit = cpu; a.split = (ncomp + cpu - 1) / cpu; best_two = two; }
     }
+    two_chain = best_two;
     a.num_units = a.num_tiles * a.split;
     if (G_ll != nullptr) {
       const long long need = (long long)a.num_tiles * R * std::max(1, n_mix);
@@ -345,14 +364,17 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
       a.lse_terms = h->lse_part; a.tile_ctr = h->tile_ctr;
     }
   }
-  const int grid = std::min(a.num_units, workers);
+  int grid = std::min(a.num_units, workers);
+  { const char* ge = std::getenv("GBNF_GRID"); if (ge && std::atoi(ge) > 0) grid = std::min(grid, std::atoi(ge)); }   // diagnostics: fewer CTAs
   h->last_grid = h->tc3 ? 2 * grid : grid;
   if (h->cfg.gemm_mode == GBNF_GEMM_FP32) {
     if (R == 64) coupling_fp32_kernel<64><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
     else if (R == 32) coupling_fp32_kernel<32><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
     else coupling_fp32_kernel<16><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
   } else {
-    int rc = h->tc3 ? tc3_launch(a, h->tc, grid, st, h->profiling) : h->tc2 ? tc2_launch(a, h->tc, grid, st, h->profiling) : tc_launch(a, h->tc, grid, st);
+    int rc = two_chain ? tc4_launch(a, h->tc4plan, grid, st, h->profiling)
+           : h->tc3 ? tc3_launch(a, h->tc, grid, st, h->profiling) : h->tc2 ? tc2_launch(a, h->tc, grid, st, h->profiling) : tc_launch(a, h->tc, grid, st);
+    h->last_two_chain = two_chain ? 1 : 0;
     if (rc != 0) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: launch configuration rejected");
   }
   h->launches++;
@@ -436,6 +458,7 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
     CREATE_TRY(tc_configure(h->tc));
     CREATE_TRY(tc2_configure());
     CREATE_TRY(tc3_configure());
+    CREATE_TRY(tc4_configure());
     if (h->tc3) h->tc3_pairs = tc3_max_pairs(h->tc, h->num_sms);
   }
 #undef CREATE_TRY
@@ -984,7 +1007,7 @@ int gbnf_get_info(gbnf_handle h, gbnf_info* out) {
   out->packed_bytes = h->w_bytes + h->f_count * 4 + h->i_count * 4;
   out->launches = h->launches;
   out->pipelined = h->tc3 ? 2 : h->tc2 ? 1 : 0;
-  out->reserved = 0;
+  out->two_chain = h->last_two_chain;
   return GBNF_OK;
 }
 

@@ -47,16 +47,30 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must never hang the GPU.  On timeout the error word is set and the kernel traps.
 constexpr long long kWaitLimitCycles = 4000000000LL;   // ~2 s at 1.9 GHz
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return;
+// The spin loop with its watchdog is kept OUT of line: the kernels have hundreds of wait sites, and their instruction footprint
+// matters (a 300 KB kernel lost a third of its tensor-core issue rate to instruction fetch at full occupancy).
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, int* err_flag, int code) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
     if (clock64() - t0 > kWaitLimitCycles) {
       if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = code;   // mapped host memory: survives the trap
       __threadfence_system();
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(smem_u32(bar), parity, err_flag, code);
 }
 
 // ---- proxy / tcgen05 fences ------------------------------------------------------------------------------
@@ -233,8 +247,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   return ok != 0;
 }
 // bounded wait on a LOCAL mbarrier whose arrivals come from the peer CTA (acquire at cluster scope)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_cluster_slow(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (clock64() - t0 > kWaitLimitCycles) {
@@ -243,6 +256,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  mbar_wait_cluster_slow(bar, parity, err_flag, code);
 }
 // bulk copy from THIS CTA's shared memory into a peer CTA's shared memory; completion (complete_tx) on the PEER's mbarrier
 __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster_addr, const void* src_smem, uint32_t bytes, uint32_t mbar_cluster_addr) {

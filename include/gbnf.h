@@ -246,7 +246,8 @@ typedef struct {
   int64_t launches;        /* kernels launched through this handle so far */
   int32_t pipelined;       /* 2: CTA-pair tensor-core kernel for h = 1024 (coupling_tc3.cuh), 1: chunk-pipelined tensor-core
                               kernel (coupling_tc2.cuh), 0: serial tensor-core / fp32 kernel */
-  int32_t reserved;
+  int32_t two_chain;       /* 1: the last coupling launch ran the two-chain schedule (coupling_tc4.cuh: Glow / affine / tanh, h = 512,
+                              an even number of components per work unit) */
 } gbnf_info;
 int gbnf_get_info(gbnf_handle h, gbnf_info* out);
 

@@ -23,12 +23,15 @@ model.eval()
 for p in model.parameters():
     p.requires_grad_(False)
 model.pack_all()
-for _ in range(3):
+for _ in range(300):      # SM clocks ramp up over the first few hundred ms: cycle counters of a cold launch are not representative
     G = model.mixture_log_density(x, cfg["C"])
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); G = model.mixture_log_density(x, cfg["C"]); e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1)
+e0.record()
+for _ in range(50):
+    G = model.mixture_log_density(x, cfg["C"])
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 50
 p = model.profile()
 tiles0 = (B + 127) // 128
 tiles_cta0 = (tiles0 + 147) // 148 if tiles0 > 148 else 1
