@@ -109,7 +109,9 @@ enum { T3_OP_OWN = 0, T3_OP_SHIP, T3_OP_L3 };
 // for the peer's ship(J), which the peer only started after ITS own(J - 1), ... -- 8 serial hops per pass, measured 99 k cycles.)
 template <class F>
 __device__ __forceinline__ void t3_schedule(int p, F&& f) {
-#pragma unroll
+  // NOT unrolled: one copy of the per-pair code.  The fully unrolled kernel was 308 KB of SASS and lost a quarter of its
+  // throughput to instruction fetch at full occupancy.
+#pragma unroll 1
   for (int m = 0; m < 4; ++m) {
     f(T3_OP_SHIP, 2 * m + 1 - p, 0);
     f(T3_OP_SHIP, 2 * m + 1 - p, 1);
@@ -301,6 +303,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           tw = T3_CLK();
           wait_epi(&misc->a0r, upar, 20);
           m_wa += T3_CLK() - tw;
+#pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             tw = T3_CLK();
             if (q >= 2) wait_epi(&misc->a1r[q - 2], upar, 22);                    // its accumulator slot has been read out
@@ -513,6 +516,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           if (et == 0) ptx::mbar_arrive_expect_tx(&misc->x3full, (uint32_t)np3 * 512u);   // this pass's partial last-layer product of the peer
           e_g += T3_CLK() - tq;
           // ---- layer 1: my 512 hidden units, chunk q -> bias + act -> fp16 pairs -> A1 quarter q ----
+#pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             tq = T3_CLK();
             t2_wait(&misc->l1f[q], upar, a.error_flag, 30, lane);
@@ -557,8 +561,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
             ptx::tc_fence_before();
             if (mm < 3) t2_warp_arrive(&misc->l3r, lane);      // slot A may take the next own chunk
           };
+#pragma unroll 1
           for (int m = 0; m < 4; ++m) {
             if (m > 0) l3read(m - 1);
+#pragma unroll
             for (int y = 0; y < 2; ++y) {
               tq = T3_CLK();
               t2_wait(&misc->l2ship[y], n_ship[y] & 1u, a.error_flag, 34, lane);

@@ -11,12 +11,14 @@
 //
 //   slot s (chain B = s & 1 starts pass P_s; chain A = the other one finishes P_{s-1}):
 //     tensor pipe : [L1(0) of P_s] [last last-layer piece of P_{s-1}] [L1(1..3), layer 2 and last-layer pieces 0..3 of P_s]
-//     epilogue    : A: last layer-2 chunk -> A: last-layer accumulator to a shared-memory stash (tensor memory is now all B's)
-//                   -> B: layer-1 chunks 0..3 -> B: layer-2 chunk 0 -> A: coupling transform out of the stash, end of component
-//                   / next gather of A (= P_{s+1}) -> B: layer-2 chunks 1..3
+//     epilogue    : A: last layer-2 chunk -> B: layer-1 chunks 0..3 -> A: coupling transform (reads A's last-layer accumulator, which
+//                   no GEMM of B touches before B's first last-layer piece) -> B: layer-2 chunks 0, 1 -> A: end of component / x
+//                   reload / gather of A's next pass (= P_{s+1}) and the staging for it -> B: layer-2 chunks 2, 3
 //   A's transform, its log-density / mixture bookkeeping, the x reload and the gather of its next pass run while the tensor
-//   pipe works through B's layer 2, where the epilogue warps used to wait; only A's last chunk epilogue (1.4 k) and B's layer-1
-//   phase (5.6 k) remain exposed per pass.
+//   pipe works through B's layer 2, where the epilogue warps used to wait; only A's last chunk epilogue (1.1 k) and B's layer-1
+//   phase (4.8 k, MUFU bound) remain exposed per pass.  Layer-1 accumulators are placed so that this needs no extra tensor
+//   memory: chunk 0 -> [128, 256), chunk 1 -> slot 0, chunk 2 -> [128, 256), chunk 3 -> slot 1 + [192, 256) (two N = 64 halves).
+//   The instruction footprint is kept small on purpose (one copy of every block, runtime chunk indices).
 //
 // Everything else -- TMEM map, weight image, ring protocol, epilogue arithmetic -- is coupling_tc2_kernel's tight (h = 512)
 // geometry with NQ = 4 layer-1 chunks and NJ = 5 layer-2 chunks (128 / 64 / 128 / 64 / 128 columns); results are bitwise
@@ -463,21 +465,28 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
     };
     // ---- asynchronous staging for pass p of a chain (just gathered, index ng): its biases and z2 table; the z1 table of the
     //      chain's pass after it ----
-    auto stage = [&](int chain, const T4Pos& p, uint32_t ng) {
+    // (the descriptor loads are issued by stage_offsets() before the gather so that their L2 round trip hides under it)
+    auto stage_offsets = [&](int chain, const T4Pos& p, uint32_t ng, long long& off) {
+      off = -1;
       const StepDesc* sd = a.steps + (p.c * K + p.k);
+      if (et < 272) off = __ldg(&sd->layer[0][0].b_off);
+      else if (et < 272 + kEpPad) off = __ldg(&sd->ep_off);
+      else if (et < 272 + 2 * kEpPad && (int)ng + 1 < npass) {
+        T4Pos p2 = p;
+        t4_pos_next(a, chain, p2);
+        off = __ldg(&a.steps[p2.c * K + p2.k].ep_off);
+      }
+    };
+    auto stage = [&](int chain, uint32_t ng, long long off) {
       if (et < 272) {
-        const float* src = a.fblob + __ldg(&sd->layer[0][0].b_off);
-        if (et < ((2 * H + np3) >> 2)) ptx::cp_async16(bias_s + chain * bstride + 4 * et, src + 4 * et);
+        if (et < ((2 * H + np3) >> 2)) ptx::cp_async16(bias_s + chain * bstride + 4 * et, a.fblob + off + 4 * et);
       } else if (et < 272 + kEpPad) {
         const int i = et - 272;
-        ptx::cp_async16(tab_s + (4 + chain) * kEpPad + i, reinterpret_cast<const float4*>(a.fblob + __ldg(&sd->ep_off)) + kEpPad + i);
+        ptx::cp_async16(tab_s + (4 + chain) * kEpPad + i, reinterpret_cast<const float4*>(a.fblob + off) + kEpPad + i);
       } else if (et < 272 + 2 * kEpPad) {
-        if ((int)ng + 1 < npass) {
-          T4Pos p2 = p;
-          t4_pos_next(a, chain, p2);
-          const StepDesc* sd2 = a.steps + (p2.c * K + p2.k);
+        if (off >= 0) {
           const int i = et - 272 - kEpPad;
-          ptx::cp_async16(tab_s + (2 * chain + ((ng + 1) & 1u)) * kEpPad + i, reinterpret_cast<const float4*>(a.fblob + __ldg(&sd2->ep_off)) + i);
+          ptx::cp_async16(tab_s + (2 * chain + ((ng + 1) & 1u)) * kEpPad + i, reinterpret_cast<const float4*>(a.fblob + off) + i);
         }
       }
     };
@@ -651,6 +660,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
       }
       if ((int)ng < npass) {
         if (!start) t4_pos_next(a, chain, p);
+        long long soff;
+        stage_offsets(chain, p, ng, soff);
         if (p.k == 0) {                      // a component starts from x (every thread loads the columns it owns)
           load_x(p, zrow);
           t2_quad_bar(quad);
@@ -661,7 +672,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
         ptx::tc_fence_before();
         t2_warp_arrive(&misc->a0r[chain], lane);
         e_ga += T4_CLK() - tg;
-        stage(chain, p, ng);
+        stage(chain, ng, soff);
         ++ng;
       }
       if (chain) { pY = p; ngY = ng; } else { pX = p; ngX = ng; }
@@ -700,7 +711,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
 #pragma unroll 1
           for (int q = 0; q < NQ; ++q) e1_chunk(q, biasB, (uint32_t)ch);
         }
-        if (t == 1 && s > 0) finish_a(fin, (uint32_t)(s - 1) & 1u);
+        // the finishing chain's transform goes where the epilogue would wait for layer-2 chunk 0 (its last k-quarter is still
+        // being multiplied); it also frees the last-layer accumulator before this pass's piece 0 needs it
+        if (t == 0 && s > 0) finish_a(fin, (uint32_t)(s - 1) & 1u);
         if (t == 2) finish_b(fin, s <= 0);
       }
       tq = T4_CLK();
