@@ -479,10 +479,19 @@ def run_ours(a):
     long_run = ms_total > 1000.0
     peak = pk["bf16_sustained"] if long_run else pk["bf16_burst"]
     achieved = fl / (k_ms * 1e-3) / 1e12
-    traffic = None
+    # DRAM bytes per launch of the dominant kernel cannot be read from inside the process (no CUPTI here): they come from the
+    # committed `ncu --set full` capture of this exact command (profiles/traffic.json names the capture per configuration)
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{a.config}:{a.mode}:{a.batch}")
+        tj = json.load(open(tpath))
+        traffic = tj.get(f"{a.config}:{a.mode}:{a.batch}")
+        src = tj.get("_source")
+        traffic_src = src.get(f"{a.config}:{a.mode}:{a.batch}") if isinstance(src, dict) else src
+    inf = model.info()
+    kname = ("coupling_fp32_kernel" if a.mode == "fp32" else "coupling_tc4_kernel (two-chain, tcgen05)" if inf.get("two_chain") else
+             "coupling_tc3_kernel (CTA pair, tcgen05)" if inf["pipelined"] == 2 else "coupling_tc2_kernel (pipelined, tcgen05)" if inf["pipelined"] == 1
+             else "coupling_tc_kernel (serial, tcgen05)")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong" if comp_par else "weak",
@@ -494,7 +503,9 @@ def run_ours(a):
                                    f"{a.batch} rows of a step; log q [B, C/G] " + ("stored by the coupling epilogue into every rank's gather buffer over NVLink peer memory" if peer else "all-gathered with NCCL") + ")" if comp_par else
                                    f"batch-parallel x{world} (weak: {a.batch} rows per GPU per step" + ("" if world == 1 else "; global softmax via " + ("the library's peer-memory exchange" if peer else "three NCCL scalar all-reduces")) + ")")},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "coupling (C/G components) + all-gather + mixture" if comp_par else "fused coupling+mixture", "kernel_ms": k_ms, "weights_ms": w_ms,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "coupling (C/G components) + all-gather + mixture" if comp_par else "fused coupling+mixture", "kernel_name": kname,
+                     "kernel_ms": k_ms, "weights_ms": w_ms,
                      "flops_per_sample": flops_per_sample(cfg),
                      "peak_kind": ("sustained" if long_run else "burst") + " bf16, " + pk["source"]},
         "clocks": clocks,
