@@ -81,7 +81,8 @@ struct CouplingArgs {
   float* lse_terms;                // [num_tiles * 128][n_mix]
   unsigned int* tile_ctr;          // [num_tiles], zero between launches (reset by the last arriver)
   // component-parallel multi-GPU (gbnf_mixture_component_parallel): when n_peers > 0 every log q value is ALSO stored into the
-  // gather buffer of every rank (peer memory over NVLink) at column peer_col0 + (c - c0) of a [B, peer_ld] matrix
+  // gather buffer of every rank (peer memory over NVLink): COMPONENT-major, element (row, peer_col0 + (c - c0)) at
+  // [(peer_col0 + c - c0) * peer_ld + row], so that the 32 rows of a warp form one 128-byte NVLink write per peer
   float* logq_peers[kMaxRanks];
   int n_peers, peer_ld, peer_col0;
   int exp_flags;                   // experiments (GBNF_EXP env, diagnostics only): bit 0 = producer skips the weight copies

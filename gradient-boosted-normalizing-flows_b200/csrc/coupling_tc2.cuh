@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc2_kernel(CouplingArg
           if (gr < a.B) {
             if (a.logq) a.logq[gr * a.ld_logq + (c - a.c0)] = lq;
             // component-parallel multi-GPU: the same value straight into every rank's gather buffer (peer memory over NVLink)
-            for (int q = 0; q < a.n_peers; ++q) a.logq_peers[q][gr * a.peer_ld + a.peer_col0 + (c - a.c0)] = lq;
+            for (int q = 0; q < a.n_peers; ++q) a.logq_peers[q][(long long)(a.peer_col0 + (c - a.c0)) * a.peer_ld + gr] = lq;
             if (a.ldj_out) a.ldj_out[gr] = ldj_tot;
           }
           if (a.G_ll != nullptr && c < a.n_mix) __stcg(a.lse_terms + ((long long)tile * kTcRows + row) * a.n_mix + c, misc->coef[c] + lq);

@@ -730,7 +730,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) coupl
           const float lq = (base_const - q) + ldj_tot;
           if (gr < a.B) {
             if (a.logq) a.logq[gr * a.ld_logq + (c - a.c0)] = lq;
-            for (int q = 0; q < a.n_peers; ++q) a.logq_peers[q][gr * a.peer_ld + a.peer_col0 + (c - a.c0)] = lq;   // see coupling_tc2.cuh
+            for (int q = 0; q < a.n_peers; ++q) a.logq_peers[q][(long long)(a.peer_col0 + (c - a.c0)) * a.peer_ld + gr] = lq;   // see coupling_tc2.cuh
             if (a.ldj_out) a.ldj_out[gr] = ldj_tot;
           }
           if (a.G_ll != nullptr && c < a.n_mix) __stcg(a.lse_terms + ((long long)tile * kTcRows + row) * a.n_mix + c, misc->coef[c] + lq);

@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
         const float lq = (cconst.y - q) + ldj_tot;
         if (gr < a.B) {
           if (a.logq) a.logq[gr * a.ld_logq + (c - a.c0)] = lq;
-          for (int qq = 0; qq < a.n_peers; ++qq) a.logq_peers[qq][gr * a.peer_ld + a.peer_col0 + (c - a.c0)] = lq;
+          for (int qq = 0; qq < a.n_peers; ++qq) a.logq_peers[qq][(long long)(a.peer_col0 + (c - a.c0)) * a.peer_ld + gr] = lq;
           if (a.ldj_out) a.ldj_out[gr] = ldj_tot;
         }
         if (a.G_ll != nullptr && c < a.n_mix) __stcg(a.lse_terms + ((long long)tile * kTcRows + row) * a.n_mix + c, misc->coef[c] + lq);

@@ -880,10 +880,11 @@ int gbnf_mixture_component_parallel(gbnf_handle h, const float* d_x, int64_t B, 
   cudaStream_t st = (cudaStream_t)stream;
   h->cv.epoch += 1;
   const int per = n_comp / world, c0 = rank * per;
-  const int ld = h->cfg.C;                                  // gather buffers are [rows, C]
+  const int ld = h->cfg.C;
+  const long long tstride = h->comm_rows;                   // gather buffers are component-major: [C][comm_rows]
   if (h->cfg.gemm_mode != GBNF_GEMM_FP32 && (h->tc2 || h->tc3)) {
     // fused: the coupling kernel's epilogue stores log q into every rank's gather buffer
-    int rc = launch_coupling(h, d_x, B, c0, c0 + per, nullptr, per, nullptr, nullptr, nullptr, 0, -1, 0, nullptr, st, true, ld, c0);
+    int rc = launch_coupling(h, d_x, B, c0, c0 + per, nullptr, per, nullptr, nullptr, nullptr, 0, -1, 0, nullptr, st, true, (int)tstride, c0);
     if (rc != GBNF_OK) return rc;
   } else {
     const long long need = (long long)B * per;
@@ -895,11 +896,11 @@ int gbnf_mixture_component_parallel(gbnf_handle h, const float* d_x, int64_t B, 
     }
     int rc = launch_coupling(h, d_x, B, c0, c0 + per, h->cp_tmp, per, nullptr, nullptr, nullptr, 0, -1, 0, nullptr, st);
     if (rc != GBNF_OK) return rc;
-    comm_scatter_logq_kernel<<<grid_for(h, need, kMixThreads), kMixThreads, 0, st>>>(h->cp_tmp, B, per, h->cv, ld, c0);
+    comm_scatter_logq_kernel<<<grid_for(h, need, kMixThreads), kMixThreads, 0, st>>>(h->cp_tmp, B, per, h->cv, tstride, c0);
     h->launches++;
   }
   const float* mine = h->cv.gather[rank] + (h->cv.epoch & 1u) * h->cv.gather_stride;
-  mixture_lse_kernel<<<grid_for(h, B, kMixThreads), kMixThreads, 0, st>>>(mine, B, ld, n_comp, d_rho, skip_c, mix_mode, d_G_ll, h->cv, h->flags);
+  mixture_lse_kernel<<<grid_for(h, B, kMixThreads), kMixThreads, 0, st>>>(mine, B, ld, n_comp, d_rho, skip_c, mix_mode, d_G_ll, h->cv, h->flags, tstride);
   h->launches++;
   CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;

@@ -53,9 +53,13 @@ __device__ __forceinline__ void mixture_rows_small(const float* __restrict__ log
 // With cv.world > 1 (component-parallel) logq is this rank's gather buffer: block 0 first publishes "my block is written"
 // (the coupling launch before this one in the stream stored it into every rank's buffer), every block then waits until all
 // ranks have published the current epoch.
+// tstride > 0: logq is COMPONENT-major, element (b, c) at logq[c * tstride + b] (the component-parallel gather buffers: every
+// rank's coupling kernel stores 128 consecutive rows of one component = 512 contiguous bytes per peer; with the row-major
+// layout each row was a separate 4-byte NVLink write, which cost 2.3 ms per step on 8 GPUs).
 __global__ void __launch_bounds__(kMixThreads) mixture_lse_kernel(const float* __restrict__ logq, long long B, int ld,
                                                                  int n, const float* __restrict__ rho, int skip_c,
-                                                                 int mix_mode, float* __restrict__ G_ll, CommView cv, int* status) {
+                                                                 int mix_mode, float* __restrict__ G_ll, CommView cv, int* status,
+                                                                 long long tstride = 0) {
   __shared__ float coef[kMaxComponents];
   __shared__ float rho_sum;
   if (cv.world > 1) {
@@ -81,6 +85,22 @@ __global__ void __launch_bounds__(kMixThreads) mixture_lse_kernel(const float* _
   __syncthreads();
   const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logq) & 15) == 0);
   const long long stride = (long long)gridDim.x * blockDim.x;
+  if (tstride > 0) {          // component-major (logsumexp modes only): coalesced across the rows of a warp
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += stride) {
+      if (n <= 16) {          // the same arithmetic as the row-major small path (exact max, then the sum)
+        float4 v[4];
+        float* t = reinterpret_cast<float*>(v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) t[c] = (c < n) ? __ldcs(logq + c * tstride + b) : 0.f;
+        G_ll[b] = mixture_row_lse<4>(v, n, coef);
+      } else {
+        OnlineLse o; o.init();
+        for (int c = 0; c < n; ++c) o.add(coef[c] + __ldcs(logq + c * tstride + b));
+        G_ll[b] = o.value();
+      }
+    }
+    return;
+  }
   if (mix_mode == GBNF_MIX_GEOMETRIC) {
     for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += stride) {
       const float* row = logq + b * ld;
@@ -352,15 +372,14 @@ __global__ void __launch_bounds__(kMixThreads) weight_renorm_kernel(float* __res
 __global__ void zero_double_kernel(double* p) { *p = 0.0; }
 
 // Component-parallel fallback for the coupling kernels that do not store into peer memory themselves: copies this rank's
-// log q block [B, nc] into columns [col0, col0 + nc) of every rank's [B, ld] gather buffer.
+// log q block [B, nc] into components [col0, col0 + nc) of every rank's COMPONENT-major gather buffer [C][tstride rows].
 __global__ void __launch_bounds__(kMixThreads) comm_scatter_logq_kernel(const float* __restrict__ local, long long B, int nc, CommView cv,
-                                                                       int ld, int col0) {
-  float* const base_off = nullptr; (void)base_off;
+                                                                       long long tstride, int col0) {
   const long long total = B * nc;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / nc; const int c = (int)(i - r * nc);
-    const float v = local[i];
-    for (int q = 0; q < cv.world; ++q) cv.gather[q][(cv.epoch & 1u) * cv.gather_stride + r * ld + col0 + c] = v;
+    const int c = (int)(i / B); const long long r = i - (long long)c * B;       // consecutive threads = consecutive rows
+    const float v = local[r * nc + c];
+    for (int q = 0; q < cv.world; ++q) cv.gather[q][(cv.epoch & 1u) * cv.gather_stride + (col0 + c) * tstride + r] = v;
   }
 }
 

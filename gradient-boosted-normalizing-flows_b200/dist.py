@@ -90,8 +90,10 @@ class KernelOps:
         return w
 
     def mixture_component_parallel(self, x, n_comp, skip_c=-1):
-        for c in range(n_comp):
-            self.model.pack_component(c)
+        world, rank = _world(None)
+        per = n_comp // max(world, 1)
+        for c in range(rank * per, (rank + 1) * per):     # only the components this rank evaluates (the staleness check of all
+            self.model.pack_component(c)                  # C components cost 2 ms of host time per step at cfg4)
         G = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
         rho = self.model.rho.detach().to(x.device, torch.float32).contiguous()
         _lib.check(self.lib.gbnf_mixture_component_parallel(self._h(x), self._p(x), x.shape[0], n_comp, self._p(rho), skip_c,

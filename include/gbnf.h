@@ -196,8 +196,10 @@ int gbnf_component_backward(gbnf_handle h, int32_t c, const gbnf_component_param
  * gbnf_comm_init.  No NCCL call sits on the data path: a rank publishes a value by storing it into every rank's
  * exchange block (cudaIpc-mapped device memory) followed by a flag word, and consumes by spinning on its own block
  * inside the kernel that needs the value (bounded: a missing peer raises watchdog code 40 after ~2 s).
- *   1. every rank: gbnf_comm_local_handle(h, max_rows, handle64)   allocates its block (+ a [2][max_rows, C] gather buffer
- *      for the component-parallel layout) and returns the 64-byte cudaIpcMemHandle_t;
+ *   1. every rank: gbnf_comm_local_handle(h, max_rows, handle64)   allocates its block (+ a COMPONENT-major [2][C][max_rows]
+ *      gather buffer for the component-parallel layout: 128 consecutive rows of one component are one contiguous NVLink
+ *      write; max_rows MUST be the same on every rank, it is the buffer's row stride) and returns the 64-byte
+ *      cudaIpcMemHandle_t;
  *   2. the caller all-gathers the handles with whatever plumbing it has (torch.distributed in gbnf_b200/dist.py);
  *   3. every rank: gbnf_comm_init(h, rank, world, handles[world][64]); a barrier; then, in the SAME order on every rank:
  *   gbnf_boost_weights_dist          batch-parallel: this rank's rows, boosting weights under the GLOBAL batch softmax
