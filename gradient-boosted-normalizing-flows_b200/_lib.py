@@ -11,7 +11,7 @@ from . import build as _build
 GBNF_MAX_LAYERS = 6
 
 KIND = {"realnvp": 0, "glow": 1}
-ACT = {"tanh": 0, "relu": 1, "mixed": 2}
+ACT = {"tanh": 0, "relu": 1, "mixed": 2, "residual": 3}
 COUPLING = {"affine": 0, "additive": 1}
 BASE_STD_NORMAL, BASE_DIAG_NORMAL = 0, 1
 GEMM = {"fp32": 0, "f16": 1, "f16fast": 2}

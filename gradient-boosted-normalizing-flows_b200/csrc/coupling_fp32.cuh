@@ -27,7 +27,8 @@ __device__ __forceinline__ float apply_act(float v) {
 
 // out[r][n] = act( sum_k in[r][k] * Wt[k][n] + bias[n] )  for r < R, n < Np.   in/out: shared, row stride ld.
 // 256 threads as 16 (rows) x 16 (cols); each thread owns TM = R/16 rows x 4 columns of a 64-column chunk.
-template <int R, int ACT>
+// IN_RELU: the input is read through max(., 0) (pre-activation residual blocks); ACCUM: out += result (the block's skip; out != in).
+template <int R, int ACT, bool IN_RELU = false, bool ACCUM = false>
 __device__ void gemm_layer_fp32(const float* __restrict__ in, float* __restrict__ out, int ld,
                                 const float* __restrict__ Wt, const float* __restrict__ bias, int Kp, int Np,
                                 float* __restrict__ Ws /* [2][32][64] */) {
@@ -60,7 +61,10 @@ __device__ void gemm_layer_fp32(const float* __restrict__ in, float* __restrict_
       for (int kk = 0; kk < kF32KT; kk += 4) {
         float4 a[TM];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(in + (ty * TM + i) * ld + kt * kF32KT + kk);
+        for (int i = 0; i < TM; ++i) {
+          a[i] = *reinterpret_cast<const float4*>(in + (ty * TM + i) * ld + kt * kF32KT + kk);
+          if (IN_RELU) { a[i].x = fmaxf(a[i].x, 0.f); a[i].y = fmaxf(a[i].y, 0.f); a[i].z = fmaxf(a[i].z, 0.f); a[i].w = fmaxf(a[i].w, 0.f); }
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 b = *reinterpret_cast<const float4*>(wsb + (kk + q) * kF32NT + tx * 4);
@@ -84,6 +88,10 @@ __device__ void gemm_layer_fp32(const float* __restrict__ in, float* __restrict_
       o.y = apply_act<ACT>(acc[i][1] + bv.y);
       o.z = apply_act<ACT>(acc[i][2] + bv.z);
       o.w = apply_act<ACT>(acc[i][3] + bv.w);
+      if (ACCUM) {
+        const float4 p = *reinterpret_cast<const float4*>(out + (ty * TM + i) * ld + n0 + tx * 4);
+        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      }
       *reinterpret_cast<float4*>(out + (ty * TM + i) * ld + n0 + tx * 4) = o;
     }
   }
@@ -95,6 +103,26 @@ __device__ void run_net_fp32(const StepDesc& sd, int net, int act_kind, int nlay
                              float* act0, float* act1, int ld, float* Ws) {
   // layer 0: act0 -> act1 ; hidden layers ping-pong ; result of the last layer is left in `act1`
   const float* wb = reinterpret_cast<const float*>(a.wblob);
+  if (act_kind == 3) {
+    // ResidualNet (models/layers.py:246-301): t = initial(x); per block t += second(relu(first(relu(t)))); out = final(t).
+    // t lives in act1 (updated in place by the accumulating GEMM), the block's hidden activation in act0.
+    const LayerDesc& L0 = sd.layer[net][0];
+    gemm_layer_fp32<R, 0>(act0, act1, ld, wb + L0.w_off, a.fblob + L0.b_off, L0.Kp, L0.Np, Ws);
+    for (int l = 1; l + 1 < nlayers; l += 2) {
+      const LayerDesc& La = sd.layer[net][l];
+      const LayerDesc& Lb = sd.layer[net][l + 1];
+      gemm_layer_fp32<R, 2, true>(act1, act0, ld, wb + La.w_off, a.fblob + La.b_off, La.Kp, La.Np, Ws);
+      gemm_layer_fp32<R, 0, false, true>(act0, act1, ld, wb + Lb.w_off, a.fblob + Lb.b_off, Lb.Kp, Lb.Np, Ws);
+    }
+    const LayerDesc& Lf = sd.layer[net][nlayers - 1];
+    gemm_layer_fp32<R, 0>(act1, act0, ld, wb + Lf.w_off, a.fblob + Lf.b_off, Lf.Kp, Lf.Np, Ws);
+    for (int i = threadIdx.x; i < R * Lf.Np; i += blockDim.x) {
+      int r = i / Lf.Np, n = i % Lf.Np;
+      act1[r * ld + n] = act0[r * ld + n];
+    }
+    __syncthreads();
+    return;
+  }
   float* src = act0;
   float* dst = act1;
   for (int l = 0; l < nlayers; ++l) {
@@ -171,7 +199,7 @@ __global__ void __launch_bounds__(kF32Threads, 1) coupling_fp32_kernel(CouplingA
             act0[r * ld + j] = (j < sd.in_dim) ? zs[r * Dv + idx1[j]] : 0.f;
           }
           __syncthreads();
-          int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
+          int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (md.act == GBNF_ACT_RESIDUAL) ? 3 : (net == 0 ? 2 : 1);
           run_net_fp32<R>(sd, net, act_kind, md.nlayers, a, act0, act1, ld, Ws);
           if (md.nnets == 2 && net == 0) {   // keep t_net output (shift) while s_net runs
             for (int i = tid; i < R * sd.out_dim; i += kF32Threads) {
@@ -290,7 +318,7 @@ __global__ void __launch_bounds__(kF32Threads, 1) coupling_fp32_inverse_kernel(C
           act0[r * ld + j] = (j < sd.in_dim) ? zs[r * Dv + idx1[j]] : 0.f;
         }
         __syncthreads();
-        int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1);
+        int act_kind = (md.act == GBNF_ACT_TANH) ? 1 : (md.act == GBNF_ACT_RELU) ? 2 : (md.act == GBNF_ACT_RESIDUAL) ? 3 : (net == 0 ? 2 : 1);
         run_net_fp32<R>(sd, net, act_kind, md.nlayers, a, act0, act1, ld, Ws);
         if (md.nnets == 2 && net == 0) {
           for (int i = tid; i < R * sd.out_dim; i += kF32Threads) {

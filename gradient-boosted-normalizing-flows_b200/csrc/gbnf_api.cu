@@ -179,7 +179,7 @@ int plan_layout(gbnf_ctx* h) {
   md.kind = c.kind; md.D = c.D; md.Dv = (c.D + 1) | 1;   // odd stride (bank-conflict free) with at least one scratch column at index D
   md.h = c.h; md.K = c.K; md.C = c.C; md.depth = c.depth;
   md.act = c.act; md.coupling = c.coupling; md.base = c.base;
-  md.nlayers = c.depth + 2;
+  md.nlayers = (c.act == GBNF_ACT_RESIDUAL) ? 2 * c.depth + 2 : c.depth + 2;
   md.nnets = (c.kind == GBNF_KIND_REALNVP) ? 2 : 1;
   const bool f16 = (c.gemm_mode != GBNF_GEMM_FP32);
   const int kq = f16 ? 16 : kF32KT, nq = f16 ? 16 : kF32NT;
@@ -397,8 +397,13 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   if (c.D < 2 || c.D >= kMaxD) return fail(GBNF_ERR_INVALID, "D must be in [2, 255]");
   if (c.h < 1 || c.K < 1 || c.C < 1 || c.C > kMaxComponents) return fail(GBNF_ERR_INVALID, "bad h / K / C");
   if (c.depth < 0 || c.depth + 2 > GBNF_MAX_LAYERS) return fail(GBNF_ERR_INVALID, "coupling_network_depth out of range");
-  if (c.act < 0 || c.act > 2 || c.coupling < 0 || c.coupling > 1 || c.base < 0 || c.base > 1)
+  if (c.act < 0 || c.act > GBNF_ACT_RESIDUAL || c.coupling < 0 || c.coupling > 1 || c.base < 0 || c.base > 1)
     return fail(GBNF_ERR_INVALID, "bad act / coupling / base");
+  if (c.act == GBNF_ACT_RESIDUAL) {
+    if (c.kind != GBNF_KIND_REALNVP) return fail(GBNF_ERR_INVALID, "ResidualNet coupling networks are RealNVP only (models/realnvp.py:59-60)");
+    if (c.depth < 1 || 2 * c.depth + 2 > GBNF_MAX_LAYERS) return fail(GBNF_ERR_INVALID, "ResidualNet: coupling_network_depth (blocks) must be 1 or 2");
+    if (c.gemm_mode != GBNF_GEMM_FP32) return fail(GBNF_ERR_INVALID, "ResidualNet coupling networks run in GBNF_GEMM_FP32 only");
+  }
   if (c.act == GBNF_ACT_MIXED && c.kind != GBNF_KIND_REALNVP) return fail(GBNF_ERR_INVALID, "mixed nets are RealNVP only");
   if (c.gemm_mode < GBNF_GEMM_FP32 || c.gemm_mode > GBNF_GEMM_F16_TC_FAST) return fail(GBNF_ERR_INVALID, "bad gemm_mode");
   int ndev = 0;
@@ -705,7 +710,7 @@ int gbnf_component_backward(gbnf_handle h, int32_t c, const gbnf_component_param
   if (!h || !p || !p->steps || !grads || !d_x || !d_dz || !d_dldj) return fail(GBNF_ERR_INVALID, "null argument");
   if (c < 0 || c >= h->cfg.C || p->n_steps != h->cfg.K) return fail(GBNF_ERR_INVALID, "bad component index / n_steps");
   const gbnf_config& cf = h->cfg;
-  if (cf.kind != GBNF_KIND_GLOW || cf.depth != 1 || cf.act == GBNF_ACT_MIXED || cf.h > 512 || cf.D > 64 || cf.K > kTrMaxK)
+  if (cf.kind != GBNF_KIND_GLOW || cf.depth != 1 || cf.act == GBNF_ACT_MIXED || cf.act == GBNF_ACT_RESIDUAL || cf.h > 512 || cf.D > 64 || cf.K > kTrMaxK)
     return fail(GBNF_ERR_INVALID, "fused backward: Glow components with coupling_network_depth 1, h <= 512, D <= 64 (others train through "
                                   "the caller's autograd)");
   if (B <= 0) return fail(GBNF_ERR_INVALID, "empty batch");

@@ -10,6 +10,9 @@ def _np(t):
 
 
 def _linears(net):
+    if hasattr(net, "initial_layer"):      # ResidualNet (models/layers.py:277-301): initial, (block first, block second)*, final
+        mods = [net.initial_layer] + [lin for b in net.blocks for lin in b.linear_layers] + [net.final_layer]
+        return [(_np(m.weight), _np(m.bias)) for m in mods]
     return [(_np(m.weight), _np(m.bias)) for m in net.network if isinstance(m, torch.nn.Linear)]
 
 

@@ -46,6 +46,49 @@ class CouplingMLP(nn.Module):
         return self.network(x)
 
 
+class ResidualBlock(nn.Module):
+    """Pre-activation ReLU block with a skip (models/layers.py:246-274): same attribute names, same RNG draws at construction
+    (two default-initialised Linears, then the second one re-drawn uniform(-1e-3, 1e-3))."""
+
+    def __init__(self, hidden_dim):
+        super().__init__()
+        self.activation = nn.ReLU()
+        self.linear_layers = nn.ModuleList([nn.Linear(hidden_dim, hidden_dim) for _ in range(2)])
+        nn.init.uniform_(self.linear_layers[-1].weight, -1e-3, 1e-3)
+        nn.init.uniform_(self.linear_layers[-1].bias, -1e-3, 1e-3)
+
+    def forward(self, inputs):
+        t = self.linear_layers[0](self.activation(inputs))
+        t = self.linear_layers[1](self.activation(t))
+        return inputs + t
+
+
+class ResidualNet(nn.Module):
+    """initial Linear -> `num_layers` residual blocks -> final Linear (models/layers.py:277-301; the s / t networks of a RealNVP
+    component with args.coupling_network == 'residual', models/realnvp.py:59-60)."""
+
+    act = "residual"
+
+    def __init__(self, in_dim, out_dim, hidden_dim, num_layers=2):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.initial_layer = nn.Linear(in_dim, hidden_dim)
+        self.blocks = nn.ModuleList([ResidualBlock(hidden_dim) for _ in range(num_layers)])
+        self.final_layer = nn.Linear(hidden_dim, out_dim)
+
+    def linears(self):
+        out = [self.initial_layer]
+        for b in self.blocks:
+            out += list(b.linear_layers)
+        return out + [self.final_layer]
+
+    def forward(self, inputs):
+        t = self.initial_layer(inputs)
+        for b in self.blocks:
+            t = b(t)
+        return self.final_layer(t)
+
+
 class ActNorm1d(nn.Module):
     """Per-feature affine with data-dependent initialisation (models/layers.py:453-545)."""
 
@@ -229,15 +272,17 @@ class RealNVPFlow(nn.Module):
         self.register_buffer("base_dist_var", 3.0 * torch.ones(D, device=args.device))
         if args.coupling_network == "mixed":
             acts = ("relu", "tanh")                     # t_net ReLU, s_net Tanh (models/realnvp.py:47-51)
-        elif args.coupling_network in _ACTS:
+        elif args.coupling_network in _ACTS or args.coupling_network == "residual":
             acts = (args.coupling_network,) * 2
         else:
-            raise NotImplementedError("coupling_network must be 'tanh', 'relu' or 'mixed' on this path")
+            raise NotImplementedError("coupling_network must be 'tanh', 'relu', 'residual' or 'mixed' on this path ('random' draws the "
+                                      "network type from numpy's global RNG upstream)")
         self.flow_param = nn.ModuleList()
         for k in range(self.num_flows):
             flipped = ((k + flip_init) % 2) > 0
             d_in, d_out = (D - D // 2, D // 2) if flipped else (D // 2, D - D // 2)
-            nets = [CouplingMLP(d_in, d_out, args.h_size, args.coupling_network_depth, a) for a in acts]
+            nets = [ResidualNet(d_in, d_out, args.h_size, args.coupling_network_depth) if a == "residual"
+                    else CouplingMLP(d_in, d_out, args.h_size, args.coupling_network_depth, a) for a in acts]
             bn = BatchNorm(D) if (args.batch_norm and k < self.num_flows - 1) else None
             self.flow_param.append(nn.ModuleList(nets + [bn]))
         self.register_buffer("prior_h", torch.zeros([1, 2 * D]))

@@ -48,7 +48,11 @@ typedef enum {
 } gbnf_status;
 
 enum { GBNF_KIND_REALNVP = 0, GBNF_KIND_GLOW = 1 };              /* models/boosted_flow.py:44-50 */
-enum { GBNF_ACT_TANH = 0, GBNF_ACT_RELU = 1, GBNF_ACT_MIXED = 2 }; /* models/realnvp.py:47-66 (mixed: t=ReLU, s=Tanh) */
+enum { GBNF_ACT_TANH = 0, GBNF_ACT_RELU = 1, GBNF_ACT_MIXED = 2, /* models/realnvp.py:47-66 (mixed: t=ReLU, s=Tanh) */
+       GBNF_ACT_RESIDUAL = 3 };   /* ResidualNet s / t networks (models/layers.py:246-301, selected at models/realnvp.py:59-60): Linear,
+                                     `depth` pre-activation ReLU blocks of two Linears with a skip, Linear = 2 depth + 2 Linear layers in
+                                     W[net][0 .. 2 depth + 1] (initial, block 0 first, block 0 second, ..., final); RealNVP only, depth <= 2,
+                                     GBNF_GEMM_FP32 only (the tensor-core kernels keep activations as fp16 MMA operands: no skip path) */
 enum { GBNF_COUPLING_AFFINE = 0, GBNF_COUPLING_ADDITIVE = 1 };     /* models/glow.py:326-338 */
 enum { GBNF_BASE_STD_NORMAL = 0, GBNF_BASE_DIAG_NORMAL = 1 };     /* utils/distributions.py:44 | generative_flow.py:38-42 */
 enum {

@@ -45,7 +45,16 @@ def _act(a, kind):
 
 
 def mlp(x, layers, act):
-    """Linear -> [act, Linear] * depth -> act -> Linear   (TanhNet :230-243 / ReLUNet :208-227)."""
+    """Linear -> [act, Linear] * depth -> act -> Linear   (TanhNet :230-243 / ReLUNet :208-227).
+    act == 'residual': ResidualNet (models/layers.py:246-301) -- layers = [initial, (block first, block second) * n, final];
+    t = initial(x); t = t + second(relu(first(relu(t)))) per block; final(t)."""
+    if act == "residual":
+        t = x @ layers[0][0].T + layers[0][1]
+        for i in range(1, len(layers) - 1, 2):
+            (Wa, ba), (Wb, bb) = layers[i], layers[i + 1]
+            u = np.maximum(t, 0) @ Wa.T + ba
+            t = t + (np.maximum(u, 0) @ Wb.T + bb)
+        return t @ layers[-1][0].T + layers[-1][1]
     a = x @ layers[0][0].T + layers[0][1]
     for W, b in layers[1:]:
         a = _act(a, act) @ W.T + b
@@ -478,7 +487,10 @@ def unflatten_model(flat):
         for k in range(K):
             p = f"c{c}.k{k}."
             def layers(nn_):
-                return [(flat[p + f"{nn_}.W{i}"], flat[p + f"{nn_}.b{i}"]) for i in range(depth + 2)]
+                n = 0                      # however many Linear layers were stored (depth + 2; ResidualNet: 2 depth + 2)
+                while p + f"{nn_}.W{n}" in flat:
+                    n += 1
+                return [(flat[p + f"{nn_}.W{i}"], flat[p + f"{nn_}.b{i}"]) for i in range(n)]
             if model["kind"] == "glow":
                 steps.append({"an_bias": flat[p + "an_bias"], "an_logs": flat[p + "an_logs"], "perm": flat[p + "perm"],
                               "net": layers("net")})
@@ -535,9 +547,10 @@ def make_synthetic_model(kind, D, C, K, h, seed=1, depth=1, act="tanh", coupling
             else:
                 flipped = ((k + c) % 2) > 0
                 i_d, o_d = (h1, h0) if flipped else (h0, h1)
-                dims = [i_d] + [h] * (depth + 1) + [o_d]
-                t = [_linear_init(rng, dims[i + 1], dims[i]) for i in range(depth + 2)]
-                s = [_linear_init(rng, dims[i + 1], dims[i]) for i in range(depth + 2)]
+                nlin = 2 * depth + 2 if act == "residual" else depth + 2      # ResidualNet: initial, 2 per block, final
+                dims = [i_d] + [h] * (nlin - 1) + [o_d]
+                t = [_linear_init(rng, dims[i + 1], dims[i]) for i in range(nlin)]
+                s = [_linear_init(rng, dims[i + 1], dims[i]) for i in range(nlin)]
                 bn = None
                 if batch_norm and k < K - 1:
                     bn = {"log_gamma": (0.1 * rng.standard_normal(D)).astype(np.float32),

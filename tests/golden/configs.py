@@ -15,6 +15,10 @@ CONFIGS = {
     # depth-2 coupling network (serial tensor-core kernel), both pinned against the reference itself
     "glow_d43_h512": (dict(kind="glow", D=43, C=2, K=2, h=512), 8, 160, False),
     "glow_d43_h128_depth2": (dict(kind="glow", D=43, C=2, K=2, h=128, coupling_network_depth=2), 9, 150, False),
+    # ResidualNet s / t networks (models/layers.py:246-301): one and two pre-activation blocks
+    "realnvp_d6_residual": (dict(kind="realnvp", D=6, C=2, K=3, h=64, coupling_network="residual"), 10, 140, False),
+    "realnvp_d5_residual2_bn": (dict(kind="realnvp", D=5, C=2, K=2, h=64, coupling_network="residual", coupling_network_depth=2,
+                                     batch_norm=True), 11, 120, False),
 }
 # fixtures whose initial state_dict is stored as per-tensor SHA-1 digests instead of values (file size)
 STATE0_DIGEST_ONLY = {"glow_d43_h512"}

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import gbnf_b200
-from conftest import GOLDEN_CASES
+from conftest import ALL_CASES as GOLDEN_CASES
 from helpers import args_for, build_model, golden_model, load_into
 from tests.golden.configs import CONFIGS
 
@@ -15,6 +15,7 @@ def _fresh(name, g):
     perm = kw.get("flow_permutation", "shuffle")
     bn = kw.get("batch_norm", False)
     a = args_for(md, "cpu", flow_permutation=perm, batch_norm=bn, rho_init=kw.get("rho_init", "decreasing"))
+    assert a.coupling_network == kw.get("coupling_network", "tanh")
     torch.manual_seed(seed)
     return gbnf_b200.BoostedFlow(a), md
 

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES
+from conftest import ALL_CASES as GOLDEN_CASES
 from helpers import golden_model, rel_err
 from oracle import gbnf_oracle as orc
 
