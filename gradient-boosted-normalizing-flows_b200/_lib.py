@@ -27,13 +27,14 @@ class GbnfError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("kind", "D", "h", "K", "C", "depth", "act", "coupling", "base", "gemm_mode",
-                                         "device", "reserved")]
+                                         "device", "glow_invconv")]
 
 
 class StepParams(C.Structure):
     _fields_ = [("an_bias", C.c_void_p), ("an_logs", C.c_void_p), ("perm", C.c_void_p),
                 ("bn_log_gamma", C.c_void_p), ("bn_beta", C.c_void_p), ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p),
-                ("W", (C.c_void_p * GBNF_MAX_LAYERS) * 2), ("b", (C.c_void_p * GBNF_MAX_LAYERS) * 2)]
+                ("W", (C.c_void_p * GBNF_MAX_LAYERS) * 2), ("b", (C.c_void_p * GBNF_MAX_LAYERS) * 2),
+                ("invconv_w", C.c_void_p), ("invconv_winv", C.c_void_p), ("invconv_logdet", C.c_void_p)]
 
 
 class StepGrads(C.Structure):
@@ -111,7 +112,7 @@ def load(rebuild_if_stale=True):
         fn = getattr(lib, name)   # AttributeError here == ABI drift, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.gbnf_abi_version() != 1:
+    if lib.gbnf_abi_version() != 2:
         raise RuntimeError("libgbnf_b200.so ABI version mismatch")
     _LIB = lib
     return lib

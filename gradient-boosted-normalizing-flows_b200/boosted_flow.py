@@ -150,7 +150,7 @@ class BoostedFlow(nn.Module):
         a = self.args
         return (self.fused_backward and x.is_cuda and x.dtype == torch.float32 and self.component_type == "glow"
                 and a.coupling_network_depth == 1 and a.h_size <= 512 and self.z_size <= 64 and a.num_flows <= 32
-                and a.coupling_network in ("tanh", "relu"))
+                and a.coupling_network in ("tanh", "relu") and getattr(a, "flow_permutation", "shuffle") != "invconv")
 
     def _component_backward(self, c, x, dz, dldj):
         """Gradients of component c's parameters for upstream (dz, dldj): {id(param): grad} (gbnf_component_backward)."""
@@ -253,12 +253,14 @@ class BoostedFlow(nn.Module):
         cfg.base = _lib.BASE_DIAG_NORMAL if self.toy_base else _lib.BASE_STD_NORMAL
         cfg.gemm_mode = _lib.GEMM[self.gemm_mode]
         cfg.device = device.index if device.index is not None else torch.cuda.current_device()
+        cfg.glow_invconv = 1 if (self.component_type == "glow" and getattr(a, "flow_permutation", "shuffle") == "invconv") else 0
         return cfg
 
     def _config_key(self):
         a = self.args
         return (self.component_type, self.z_size, a.h_size, a.num_flows, self.num_components, a.coupling_network_depth,
-                a.coupling_network, getattr(a, "flow_coupling", "affine"), self.toy_base, self.gemm_mode)
+                a.coupling_network, getattr(a, "flow_coupling", "affine"), getattr(a, "flow_permutation", "shuffle"), self.toy_base,
+                self.gemm_mode)
 
     def handle(self, device=None):
         device = torch.device(device) if device is not None else self.rho.device
@@ -319,7 +321,16 @@ class BoostedFlow(nn.Module):
                 if not step.actnorm.inited:
                     raise ValueError("In Eval mode, but ActNorm not initiated")   # models/layers.py:474-475
                 d["an_bias"], d["an_logs"] = step.actnorm.bias, step.actnorm.logs
-                d["perm"] = step.permutation.indices
+                if hasattr(step, "invconv"):
+                    # the dense weight, its inverse (fp64 inversion) and dlogdet, formed from the module's factors at pack time
+                    # (tiny D x D host-side algebra, off the hot path; models/layers.py:751-779)
+                    with torch.no_grad():
+                        w, dl = step.invconv.get_weight()
+                        d["invconv"] = (w.detach().float().contiguous(),
+                                        torch.linalg.inv(w.detach().double()).float().contiguous(),
+                                        dl.detach().float().reshape(1).contiguous())
+                else:
+                    d["perm"] = step.permutation.indices
                 d["nets"] = [step.block.linears()]
             else:
                 t_net, s_net, bn = step[0], step[1], step[2]
@@ -335,8 +346,9 @@ class BoostedFlow(nn.Module):
             sig.append((t.data_ptr(), t._version))
         if self.component_type == "glow":
             for s in self.flows[c].steps():
-                idx = s.permutation.indices
-                sig.append((id(idx), idx._version))
+                if s.permutation is not None:
+                    idx = s.permutation.indices
+                    sig.append((id(idx), idx._version))
         return tuple(sig)
 
     def pack_component(self, c, force=False):
@@ -367,7 +379,10 @@ class BoostedFlow(nn.Module):
             sp = arr[k]
             if "an_bias" in d:
                 sp.an_bias, sp.an_logs = dev(d["an_bias"].reshape(-1)), dev(d["an_logs"].reshape(-1))
-                sp.perm = dev(d["perm"], torch.int64)
+                if "invconv" in d:
+                    sp.invconv_w, sp.invconv_winv, sp.invconv_logdet = [dev(t) for t in d["invconv"]]
+                else:
+                    sp.perm = dev(d["perm"], torch.int64)
             if "bn" in d:
                 sp.bn_log_gamma, sp.bn_beta, sp.bn_mean, sp.bn_var = [dev(t) for t in d["bn"]]
             for n, lins in enumerate(d["nets"]):

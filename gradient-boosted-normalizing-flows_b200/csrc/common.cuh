@@ -34,7 +34,7 @@ struct LayerDesc {
 struct StepDesc {
   int in_dim, out_dim;   // |z1| (MLP input), |z2| (transformed half)
   int has_affine;        // ActNorm1d (glow) or eval-mode BatchNorm (realnvp) present
-  int pad_;
+  int has_invconv;       // Glow: a dense D x D step (InvertibleConv1x1) follows the ActNorm instead of a permutation (fp32 path)
   long long vec_off;     // fblob: add[Dv] | mul[Dv] | off[Dv]  (physical column order), y = (z + add) * mul + off
   long long idx_off;     // iblob: idx1[in_dim] | idx2[out_dim]  physical columns of z1 / z2
   // Branch-free tables of the pipelined tensor-core kernel, in GATHER order and padded to kEpPad entries:
@@ -43,6 +43,10 @@ struct StepDesc {
   //                     tables of the INVERSE affine {-off, 1 / mul, -add, column}[kEpPad] (sampling direction)
   long long ep_off;
   long long eidx_off;
+  // invconv (fp32 path): wblob float offsets of the forward / inverse matrices in the GEMM layout Wt[Kp][Np] (k = physical input
+  // column, n = physical output column; the permutation composed so far is folded in at pack time) and a zero bias [Np] in fblob
+  long long icw_off, icwinv_off, icb_off;
+  int ic_Kp, ic_Np;
   LayerDesc layer[2][GBNF_MAX_LAYERS];   // net 0: glow block / realnvp t_net; net 1: realnvp s_net
 };
 

@@ -98,6 +98,24 @@ __device__ void gemm_layer_fp32(const float* __restrict__ in, float* __restrict_
   __syncthreads();
 }
 
+// Dense D x D step (InvertibleConv1x1 on feature vectors, models/layers.py:781-796): zs[:, 0:D] <- zs[:, 0:D] . M through the
+// activation buffers; M = Wt[Kp][Np] in the GEMM layout with the lazy permutation folded in at pack time (pack_meta_kernel).
+template <int R>
+__device__ void dense_step_fp32(float* zs, int Dv, int D, const float* M, const float* zero_bias, int Kp, int Np,
+                                float* act0, float* act1, int ld, float* Ws) {
+  for (int i = threadIdx.x; i < R * Kp; i += blockDim.x) {
+    int r = i / Kp, j = i % Kp;
+    act0[r * ld + j] = (j < D) ? zs[r * Dv + j] : 0.f;
+  }
+  __syncthreads();
+  gemm_layer_fp32<R, 0>(act0, act1, ld, M, zero_bias, Kp, Np, Ws);
+  for (int i = threadIdx.x; i < R * D; i += blockDim.x) {
+    int r = i / D, j = i % D;
+    zs[r * Dv + j] = act1[r * ld + j];
+  }
+  __syncthreads();
+}
+
 template <int R>
 __device__ void run_net_fp32(const StepDesc& sd, int net, int act_kind, int nlayers, const CouplingArgs& a,
                              float* act0, float* act1, int ld, float* Ws) {
@@ -192,6 +210,9 @@ __global__ void __launch_bounds__(kF32Threads, 1) coupling_fp32_kernel(CouplingA
           }
           __syncthreads();
         }
+        if (sd.has_invconv)
+          dense_step_fp32<R>(zs, Dv, D, reinterpret_cast<const float*>(a.wblob) + sd.icw_off, a.fblob + sd.icb_off, sd.ic_Kp, sd.ic_Np,
+                             act0, act1, ld, Ws);
         const int Kp0 = sd.layer[0][0].Kp;
         for (int net = 0; net < md.nnets; ++net) {
           for (int i = tid; i < R * Kp0; i += kF32Threads) {
@@ -354,6 +375,9 @@ __global__ void __launch_bounds__(kF32Threads, 1) coupling_fp32_inverse_kernel(C
         ldj[r] = l;
       }
       __syncthreads();
+      if (sd.has_invconv)                                              // W^-1 (layers.py:772-776), back to the pre-step column layout
+        dense_step_fp32<R>(zs, Dv, D, reinterpret_cast<const float*>(a.wblob) + sd.icwinv_off, a.fblob + sd.icb_off, sd.ic_Kp, sd.ic_Np,
+                           act0, act1, ld, Ws);
       if (sd.has_affine) {                                             // ActNorm reverse (layers.py:505-518) / BatchNorm^-1
         for (int i = tid; i < R * D; i += kF32Threads) {
           int r = i / D, p = i % D;

@@ -61,6 +61,7 @@ struct gbnf_ctx {
   std::vector<StepDesc> steps_h;
   std::vector<CompDesc> comps_h;
   std::vector<char> packed;
+  std::vector<char> inv_ok;      // invconv components: 0 when the pack came without the inverse matrices
   StepDesc* steps_d = nullptr;
   CompDesc* comps_d = nullptr;
   float* fblob = nullptr;
@@ -201,6 +202,14 @@ int plan_layout(gbnf_ctx* h) {
       f = round_up_ll(f, 4);
       sd.ep_off = f; f += 16LL * kEpPad;
       sd.eidx_off = 0;
+      sd.has_invconv = (c.kind == GBNF_KIND_GLOW && c.glow_invconv) ? 1 : 0;
+      if (sd.has_invconv) {
+        sd.ic_Kp = round_up(c.D, kF32KT); sd.ic_Np = round_up(c.D, kF32NT);
+        sd.icw_off = w; w += (long long)sd.ic_Kp * sd.ic_Np;
+        sd.icwinv_off = w; w += (long long)sd.ic_Kp * sd.ic_Np;
+        sd.icb_off = f; f += round_up_ll(sd.ic_Np, 4);
+        kp0_max = std::max(kp0_max, sd.ic_Kp); np_last_max = std::max(np_last_max, sd.ic_Np);   // the dense step goes through the activation buffers
+      }
       h->out_max = std::max(h->out_max, sd.out_dim);
       int n_last = sd.out_dim;
       if (c.kind == GBNF_KIND_GLOW && c.coupling == GBNF_COUPLING_AFFINE) n_last = 2 * sd.out_dim;
@@ -400,12 +409,16 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   if (c.act < 0 || c.act > GBNF_ACT_RESIDUAL || c.coupling < 0 || c.coupling > 1 || c.base < 0 || c.base > 1)
     return fail(GBNF_ERR_INVALID, "bad act / coupling / base");
   if (c.act == GBNF_ACT_RESIDUAL) {
-    if (c.kind != GBNF_KIND_REALNVP) return fail(GBNF_ERR_INVALID, "ResidualNet coupling networks are RealNVP only (models/realnvp.py:59-60)");
+    if (c.kind != GBNF_KIND_REALNVP) return fail(GBNF_ERR_INVALID, "ResidualNet coupling networks are RealNVP only (upstream's Glow cannot build them: models/glow.py:294)");
     if (c.depth < 1 || 2 * c.depth + 2 > GBNF_MAX_LAYERS) return fail(GBNF_ERR_INVALID, "ResidualNet: coupling_network_depth (blocks) must be 1 or 2");
     if (c.gemm_mode != GBNF_GEMM_FP32) return fail(GBNF_ERR_INVALID, "ResidualNet coupling networks run in GBNF_GEMM_FP32 only");
   }
   if (c.act == GBNF_ACT_MIXED && c.kind != GBNF_KIND_REALNVP) return fail(GBNF_ERR_INVALID, "mixed nets are RealNVP only");
   if (c.gemm_mode < GBNF_GEMM_FP32 || c.gemm_mode > GBNF_GEMM_F16_TC_FAST) return fail(GBNF_ERR_INVALID, "bad gemm_mode");
+  if (c.glow_invconv != 0 && c.glow_invconv != 1) return fail(GBNF_ERR_INVALID, "glow_invconv must be 0 or 1");
+  if (c.glow_invconv && c.kind != GBNF_KIND_GLOW) return fail(GBNF_ERR_INVALID, "glow_invconv needs kind == GBNF_KIND_GLOW");
+  if (c.glow_invconv && c.gemm_mode != GBNF_GEMM_FP32)
+    return fail(GBNF_ERR_INVALID, "Glow steps with an invertible 1x1 convolution run in GBNF_GEMM_FP32 only");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -423,6 +436,7 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
   int rc = plan_layout(h);
   if (rc != GBNF_OK) { delete h; return rc; }
   h->packed.assign((size_t)c.C, 0);
+  h->inv_ok.assign((size_t)c.C, 1);
 #define CREATE_TRY(expr)                                                                                 \
   do {                                                                                                   \
     cudaError_t e_ = (expr);                                                                             \
@@ -511,10 +525,17 @@ int gbnf_pack_component(gbnf_handle h, int32_t c, const gbnf_component_params* p
   const ModelDims& md = h->md;
   const bool f16 = (h->cfg.gemm_mode != GBNF_GEMM_FP32);
   StepDesc* sd_h = &h->steps_h[(size_t)c * md.K];
+  h->inv_ok[c] = 1;
   for (int k = 0; k < md.K; ++k) {
     const gbnf_step_params& sp = p->steps[k];
     if (h->cfg.kind == GBNF_KIND_GLOW) {
-      if (!sp.an_bias || !sp.an_logs || !sp.perm) return fail(GBNF_ERR_INVALID, "glow step needs an_bias / an_logs / perm");
+      if (!sp.an_bias || !sp.an_logs) return fail(GBNF_ERR_INVALID, "glow step needs an_bias / an_logs");
+      if (h->cfg.glow_invconv) {
+        if (!sp.invconv_w || !sp.invconv_logdet) return fail(GBNF_ERR_INVALID, "glow_invconv: the step needs invconv_w and invconv_logdet");
+        if (!sp.invconv_winv) h->inv_ok[c] = 0;
+      } else if (!sp.perm) {
+        return fail(GBNF_ERR_INVALID, "glow step needs perm");
+      }
       sd_h[k].has_affine = 1;
     } else {
       const int nbn = (sp.bn_log_gamma != nullptr) + (sp.bn_beta != nullptr) + (sp.bn_mean != nullptr) + (sp.bn_var != nullptr);
@@ -531,6 +552,7 @@ int gbnf_pack_component(gbnf_handle h, int32_t c, const gbnf_component_params* p
   PackMetaArgs ma{};
   ma.steps = h->step_params_d; ma.sdesc = h->steps_d + (size_t)c * md.K; ma.cdesc = h->comps_h[c]; ma.md = md;
   ma.flip_init = p->flip_init; ma.base_mean = h->base_mean; ma.base_scale = h->base_scale; ma.fblob = h->fblob; ma.iblob = h->iblob;
+  ma.wblob_f32 = f16 ? nullptr : (float*)h->wblob;
   pack_meta_kernel<<<1, 32, 0, st>>>(ma);
   h->launches++;
   for (int k = 0; k < md.K; ++k) {
@@ -580,6 +602,8 @@ int gbnf_component_inverse(gbnf_handle h, const float* d_z, int64_t B, int32_t c
   if (B == 0) return GBNF_OK;
   if (!d_z || !d_x) return fail(GBNF_ERR_INVALID, "null pointer");
   if (!h->packed[c]) return fail(GBNF_ERR_STATE, "component " + std::to_string(c) + " has not been packed");
+  if (h->cfg.glow_invconv && !h->inv_ok[c])
+    return fail(GBNF_ERR_STATE, "inverse direction: component " + std::to_string(c) + " was packed without invconv_winv");
   const bool f16 = h->cfg.gemm_mode != GBNF_GEMM_FP32;
   if (f16 && !h->tc2)
     return fail(GBNF_ERR_INVALID, "inverse direction: the f16 tensor-core modes serve it through the pipelined kernel only (hidden width a "
@@ -710,7 +734,7 @@ int gbnf_component_backward(gbnf_handle h, int32_t c, const gbnf_component_param
   if (!h || !p || !p->steps || !grads || !d_x || !d_dz || !d_dldj) return fail(GBNF_ERR_INVALID, "null argument");
   if (c < 0 || c >= h->cfg.C || p->n_steps != h->cfg.K) return fail(GBNF_ERR_INVALID, "bad component index / n_steps");
   const gbnf_config& cf = h->cfg;
-  if (cf.kind != GBNF_KIND_GLOW || cf.depth != 1 || cf.act == GBNF_ACT_MIXED || cf.act == GBNF_ACT_RESIDUAL || cf.h > 512 || cf.D > 64 || cf.K > kTrMaxK)
+  if (cf.kind != GBNF_KIND_GLOW || cf.glow_invconv || cf.depth != 1 || cf.act == GBNF_ACT_MIXED || cf.act == GBNF_ACT_RESIDUAL || cf.h > 512 || cf.D > 64 || cf.K > kTrMaxK)
     return fail(GBNF_ERR_INVALID, "fused backward: Glow components with coupling_network_depth 1, h <= 512, D <= 64 (others train through "
                                   "the caller's autograd)");
   if (B <= 0) return fail(GBNF_ERR_INVALID, "empty batch");

@@ -15,6 +15,7 @@ struct PackMetaArgs {
   const float* base_scale;
   float* fblob;
   int* iblob;
+  float* wblob_f32;                // invconv matrices (fp32 path only)
 };
 
 // Composes the permutations / flips of one component and writes, per step, the elementwise affine constants in
@@ -43,8 +44,26 @@ __global__ void pack_meta_kernel(PackMetaArgs a) {
         mul[sigma[j]] = expf(sp.an_logs[j]);
         ldj_const += (double)sp.an_logs[j];
       }
-      for (int j = 0; j < D; ++j) tmp[j] = sigma[(int)sp.perm[j]];
-      for (int j = 0; j < D; ++j) sigma[j] = tmp[j];
+      if (sd.has_invconv) {
+        // InvertibleConv1x1 on a feature vector (models/layers.py:781-796 with h = w = 1): z_new[i] = sum_j W[i][j] y[j], y in the
+        // LOGICAL order (y[j] sits at physical column sigma[j]).  Forward matrix M[k = sigma[j]][n = i] = W[i][j]; the result is
+        // stored in logical order, i.e. the physical layout becomes the identity.  Inverse: y[j] = sum_i Winv[j][i] z[i], written
+        // back to physical column sigma[j]: Minv[k = i][n = sigma[j]] = Winv[j][i].
+        float* M = a.wblob_f32 + sd.icw_off;
+        float* Mi = a.wblob_f32 + sd.icwinv_off;
+        for (int i = 0; i < sd.ic_Kp * sd.ic_Np; ++i) { M[i] = 0.f; Mi[i] = 0.f; }
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            M[sigma[j] * sd.ic_Np + i] = sp.invconv_w[i * D + j];
+            if (sp.invconv_winv != nullptr) Mi[i * sd.ic_Np + sigma[j]] = sp.invconv_winv[j * D + i];
+          }
+        for (int n = 0; n < sd.ic_Np; ++n) a.fblob[sd.icb_off + n] = 0.f;
+        ldj_const += (double)sp.invconv_logdet[0];
+        for (int j = 0; j < D; ++j) sigma[j] = j;
+      } else {
+        for (int j = 0; j < D; ++j) tmp[j] = sigma[(int)sp.perm[j]];
+        for (int j = 0; j < D; ++j) sigma[j] = tmp[j];
+      }
       for (int j = 0; j < h0; ++j) idx1[j] = sigma[j];
       for (int j = 0; j < h1; ++j) idx2[j] = sigma[h0 + j];
     } else {

@@ -29,9 +29,16 @@ def extract_model(model, toy_base=False):
         steps = []
         if kind == "glow":
             for st in flow.flow.layers:
-                perm = st.shuffle if hasattr(st, "shuffle") else st.reverse
-                steps.append({"an_bias": _np(st.actnorm.bias).reshape(-1), "an_logs": _np(st.actnorm.logs).reshape(-1),
-                              "perm": _np(perm.indices).astype(np.int64), "net": _linears(st.block)})
+                d = {"an_bias": _np(st.actnorm.bias).reshape(-1), "an_logs": _np(st.actnorm.logs).reshape(-1), "net": _linears(st.block)}
+                if hasattr(st, "invconv"):        # InvertibleConv1x1 factors as the module holds them (models/layers.py:722-749)
+                    ic = st.invconv
+                    d["perm"] = None
+                    d["ic"] = ({"p": _np(ic.p), "sign_s": _np(ic.sign_s), "lower": _np(ic.lower), "log_s": _np(ic.log_s), "upper": _np(ic.upper)}
+                               if ic.LU_decomposed else {"weight": _np(ic.weight)})
+                else:
+                    perm = st.shuffle if hasattr(st, "shuffle") else st.reverse
+                    d["perm"] = _np(perm.indices).astype(np.int64)
+                steps.append(d)
         else:
             for (t_net, s_net, bn) in flow.flow_param:
                 b = None

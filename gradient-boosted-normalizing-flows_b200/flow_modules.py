@@ -151,19 +151,62 @@ class Permute1d(nn.Module):
         return x[:, self.indices.to(x.device)]
 
 
-class GlowStep(nn.Module):
-    """ActNorm1d -> Permute1d -> affine/additive coupling (models/glow.py:261-342, 1-D branch)."""
+class InvertibleConv1x1(nn.Module):
+    """Glow's invertible 1x1 convolution (models/layers.py:722-796) on FEATURE VECTORS: same parameters / buffers and the same RNG
+    draws as upstream's constructor (torch.qr of a random matrix, then its LU factors), same weight formula; upstream's forward
+    unpacks a 4-D shape (:751) and therefore crashes on the tabular path -- here a [B, D] input is the h = w = 1 case of it:
+    z = x W^T, logdet += sum(log_s) (or slogdet(weight))."""
 
-    def __init__(self, dim, hidden_dim, actnorm_scale, flow_permutation, flow_coupling, coupling_network, depth):
+    def __init__(self, num_dim, LU_decomposed):
         super().__init__()
-        if flow_permutation not in ("shuffle", "reverse"):
-            # upstream's "invconv" crashes on 1-D data (models/layers.py:751 unpacks a 4-D shape)
-            raise NotImplementedError("1-D Glow supports flow_permutation 'shuffle' or 'reverse'")
+        w_shape = [num_dim, num_dim]
+        w_init = torch.qr(torch.randn(*w_shape))[0]
+        if not LU_decomposed:
+            self.weight = nn.Parameter(torch.Tensor(w_init))
+        else:
+            p, lower, upper = torch.lu_unpack(*torch.lu(w_init))
+            s = torch.diag(upper)
+            self.register_buffer("p", p)
+            self.register_buffer("sign_s", torch.sign(s))
+            self.lower = nn.Parameter(lower)
+            self.log_s = nn.Parameter(torch.log(torch.abs(s)))
+            self.upper = nn.Parameter(torch.triu(upper, 1))
+            self.l_mask = torch.tril(torch.ones(w_shape), -1)
+            self.eye = torch.eye(*w_shape)
+        self.w_shape = w_shape
+        self.LU_decomposed = LU_decomposed
+
+    def get_weight(self):
+        """(W [D, D], dlogdet) of the forward direction (models/layers.py:751-779 with h * w == 1)."""
+        if not self.LU_decomposed:
+            return self.weight, torch.slogdet(self.weight)[1]
+        l_mask, eye = self.l_mask.to(self.lower.device), self.eye.to(self.lower.device)
+        lower = self.lower * l_mask + eye
+        u = self.upper * l_mask.transpose(0, 1).contiguous()
+        u = u + torch.diag(self.sign_s * torch.exp(self.log_s))
+        return torch.matmul(self.p, torch.matmul(lower, u)), torch.sum(self.log_s)
+
+    def forward(self, x, logdet):
+        w, dlogdet = self.get_weight()
+        return x @ w.t(), logdet + dlogdet
+
+
+class GlowStep(nn.Module):
+    """ActNorm1d -> Permute1d | InvertibleConv1x1 -> affine/additive coupling (models/glow.py:261-342, 1-D branch)."""
+
+    def __init__(self, dim, hidden_dim, actnorm_scale, flow_permutation, flow_coupling, coupling_network, depth, LU_decomposed=True):
+        super().__init__()
+        if flow_permutation not in ("shuffle", "reverse", "invconv"):
+            raise NotImplementedError("flow_permutation must be 'shuffle', 'reverse' or 'invconv'")
         if coupling_network not in _ACTS:
+            # upstream: 'residual' raises NameError for Glow (models/glow.py:294 uses ResidualNet without importing it), 'random' draws
+            # the network type from numpy's global RNG
             raise NotImplementedError("1-D Glow coupling_network must be 'tanh' or 'relu'")
         self.flow_coupling = flow_coupling
         self.actnorm = ActNorm1d(dim, actnorm_scale)
-        if flow_permutation == "shuffle":
+        if flow_permutation == "invconv":
+            self.invconv = InvertibleConv1x1(dim, LU_decomposed=LU_decomposed)
+        elif flow_permutation == "shuffle":
             self.shuffle = Permute1d(dim, shuffle=True)
         else:
             self.reverse = Permute1d(dim, shuffle=False)
@@ -173,11 +216,16 @@ class GlowStep(nn.Module):
 
     @property
     def permutation(self):
+        if hasattr(self, "invconv"):
+            return None
         return self.shuffle if hasattr(self, "shuffle") else self.reverse
 
     def forward_autograd(self, x, logdet):
         y, logdet = self.actnorm(x, logdet)
-        y = self.permutation(y)
+        if hasattr(self, "invconv"):
+            y, logdet = self.invconv(y, logdet)
+        else:
+            y = self.permutation(y)
         d_in = y.shape[1] // 2
         y1, y2 = y[:, :d_in], y[:, d_in:]
         out = self.block(y1)
@@ -209,7 +257,8 @@ class Glow(nn.Module):
         self.z_size = args.z_size
         self.flow = GlowNet(args.input_size[0], args.h_size, args.num_flows, actnorm_scale=args.actnorm_scale,
                             flow_permutation=args.flow_permutation, flow_coupling=args.flow_coupling,
-                            coupling_network=args.coupling_network, depth=args.coupling_network_depth)
+                            coupling_network=args.coupling_network, depth=args.coupling_network_depth,
+                            LU_decomposed=getattr(args, "LU_decomposed", True))
         self.register_buffer("prior_h", torch.zeros([1, args.z_size * 2]))
         self.register_buffer("bounds", torch.tensor([0.9], dtype=torch.float32))
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GBNF_ABI_VERSION 1
+#define GBNF_ABI_VERSION 2   /* 2: gbnf_step_params.invconv_*, gbnf_config.glow_invconv, GBNF_ACT_RESIDUAL */
 #define GBNF_MAX_LAYERS 6 /* depth + 2 <= 6 */
 
 typedef struct gbnf_ctx* gbnf_handle;
@@ -49,9 +49,10 @@ typedef enum {
 
 enum { GBNF_KIND_REALNVP = 0, GBNF_KIND_GLOW = 1 };              /* models/boosted_flow.py:44-50 */
 enum { GBNF_ACT_TANH = 0, GBNF_ACT_RELU = 1, GBNF_ACT_MIXED = 2, /* models/realnvp.py:47-66 (mixed: t=ReLU, s=Tanh) */
-       GBNF_ACT_RESIDUAL = 3 };   /* ResidualNet s / t networks (models/layers.py:246-301, selected at models/realnvp.py:59-60): Linear,
+       GBNF_ACT_RESIDUAL = 3 };   /* ResidualNet coupling networks (models/layers.py:246-301, selected at models/realnvp.py:59-60): Linear,
                                      `depth` pre-activation ReLU blocks of two Linears with a skip, Linear = 2 depth + 2 Linear layers in
-                                     W[net][0 .. 2 depth + 1] (initial, block 0 first, block 0 second, ..., final); RealNVP only, depth <= 2,
+                                     W[net][0 .. 2 depth + 1] (initial, block 0 first, block 0 second, ..., final); RealNVP only (upstream's Glow
+                                     names ResidualNet without importing it, models/glow.py:294); depth <= 2,
                                      GBNF_GEMM_FP32 only (the tensor-core kernels keep activations as fp16 MMA operands: no skip path) */
 enum { GBNF_COUPLING_AFFINE = 0, GBNF_COUPLING_ADDITIVE = 1 };     /* models/glow.py:326-338 */
 enum { GBNF_BASE_STD_NORMAL = 0, GBNF_BASE_DIAG_NORMAL = 1 };     /* utils/distributions.py:44 | generative_flow.py:38-42 */
@@ -82,7 +83,9 @@ typedef struct {
   int32_t base;      /* GBNF_BASE_* */
   int32_t gemm_mode; /* GBNF_GEMM_* */
   int32_t device;    /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t glow_invconv; /* 1: the Glow steps mix the channels with InvertibleConv1x1 (args.flow_permutation == 'invconv',
+                           models/glow.py:275-278, models/layers.py:722-796) instead of Permute1d: a dense D x D step fused between
+                           ActNorm and the coupling; gbnf_step_params.invconv_* are read and perm is ignored; GBNF_GEMM_FP32 only */
 } gbnf_config;
 
 /* Raw fp32 parameters of ONE coupling step, as they sit in the reference modules' tensors (device pointers).
@@ -101,6 +104,13 @@ typedef struct {
   const float* bn_var;
   const float* W[2][GBNF_MAX_LAYERS];
   const float* b[2][GBNF_MAX_LAYERS];
+  /* Glow with config.glow_invconv: the step's 1x1 convolution weight as InvertibleConv1x1.get_weight(reverse=False) returns it
+   * (models/layers.py:751-779; LU-decomposed or plain), [D, D] row-major, z_out[i] = sum_j w[i][j] z_in[j]; its inverse (NULL:
+   * the sampling direction is refused for this component); and ONE float = dlogdet for a feature vector (sum(log_s) or
+   * slogdet(weight)).  NULL for every other configuration. */
+  const float* invconv_w;
+  const float* invconv_winv;
+  const float* invconv_logdet;
 } gbnf_step_params;
 
 typedef struct {

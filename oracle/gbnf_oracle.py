@@ -64,14 +64,34 @@ def mlp(x, layers, act):
 # --------------------------------------------------------------------------------------
 # A.2  Glow 1-D step                                   models/glow.py:317-342
 # --------------------------------------------------------------------------------------
+def invconv_weight(ic):
+    """InvertibleConv1x1.get_weight(reverse=False) for a feature vector (h * w == 1): (W [D, D], dlogdet).
+    models/layers.py:751-779.  ic = {'weight'} (plain) or {'p', 'lower', 'upper', 'log_s', 'sign_s'} (LU-decomposed)."""
+    if "weight" in ic:
+        W = ic["weight"]
+        return W, np.linalg.slogdet(W.astype(np.float64))[1].astype(W.dtype)
+    D = ic["log_s"].shape[0]
+    dt = ic["lower"].dtype
+    l_mask = np.tril(np.ones((D, D), dtype=dt), -1)
+    lower = ic["lower"] * l_mask + np.eye(D, dtype=dt)
+    u = ic["upper"] * l_mask.T + np.diag(ic["sign_s"] * np.exp(ic["log_s"]))
+    return ic["p"] @ (lower @ u), np.sum(ic["log_s"])
+
+
 def glow_step(z, ldj, step, coupling="affine", act="tanh"):
     D = z.shape[1]
     h0 = D // 2
     # 1. ActNorm1d: center then scale, logdet += sum(logs)       models/layers.py:488-518
     y = (z + step["an_bias"]) * np.exp(step["an_logs"])
     ldj = ldj + np.sum(step["an_logs"])
-    # 2. Permute1d: output column j = input column indices[j]     models/layers.py:661-668
-    y = y[:, step["perm"]]
+    if step.get("ic") is not None:
+        # 2'. InvertibleConv1x1 (F.conv2d with a [D, D, 1, 1] kernel on a 1 x 1 image): z_i = sum_j W_ij y_j   layers.py:781-796
+        W, dlogdet = invconv_weight(step["ic"])
+        y = y @ W.T
+        ldj = ldj + dlogdet
+    else:
+        # 2. Permute1d: output column j = input column indices[j]     models/layers.py:661-668
+        y = y[:, step["perm"]]
     # 3. coupling                                                 models/glow.py:326-340
     z1, z2 = y[:, :h0], y[:, h0:]
     hh = mlp(z1, step["net"], act)
@@ -152,8 +172,13 @@ def glow_step_inverse(y, ldj, step, coupling="affine", act="tanh"):
         z2 = z2 / scale - shift                                   # glow.py:354-356
         ldj = ldj - np.sum(np.log(scale), axis=1)                 # glow.py:357
     z = np.concatenate([z1, z2], axis=1)
-    zin = np.empty_like(z)
-    zin[:, step["perm"]] = z                                      # inverse of y = z[:, indices], layers.py:661-668
+    if step.get("ic") is not None:
+        W, dlogdet = invconv_weight(step["ic"])
+        zin = z @ np.linalg.inv(W.astype(np.float64)).astype(z.dtype).T      # layers.py:772-776, 791-795
+        ldj = ldj - dlogdet
+    else:
+        zin = np.empty_like(z)
+        zin[:, step["perm"]] = z                                  # inverse of y = z[:, indices], layers.py:661-668
     x = zin * np.exp(-step["an_logs"]) - step["an_bias"]          # ActNorm reverse: scale then center, layers.py:505-518
     return x, ldj - np.sum(step["an_logs"])
 
@@ -463,7 +488,12 @@ def flatten_model(model):
         for k, st in enumerate(comp["steps"]):
             p = f"c{c}.k{k}."
             if model["kind"] == "glow":
-                flat[p + "an_bias"], flat[p + "an_logs"], flat[p + "perm"] = st["an_bias"], st["an_logs"], st["perm"]
+                flat[p + "an_bias"], flat[p + "an_logs"] = st["an_bias"], st["an_logs"]
+                if st.get("ic") is not None:
+                    for n_, v in st["ic"].items():
+                        flat[p + "ic." + n_] = v
+                else:
+                    flat[p + "perm"] = st["perm"]
                 nets = {"net": st["net"]}
             else:
                 if st.get("bn") is not None:
@@ -492,8 +522,9 @@ def unflatten_model(flat):
                     n += 1
                 return [(flat[p + f"{nn_}.W{i}"], flat[p + f"{nn_}.b{i}"]) for i in range(n)]
             if model["kind"] == "glow":
-                steps.append({"an_bias": flat[p + "an_bias"], "an_logs": flat[p + "an_logs"], "perm": flat[p + "perm"],
-                              "net": layers("net")})
+                ic = {n_[len(p) + 3:]: v for n_, v in flat.items() if n_.startswith(p + "ic.")}
+                steps.append({"an_bias": flat[p + "an_bias"], "an_logs": flat[p + "an_logs"],
+                              "perm": flat[p + "perm"] if not ic else None, "ic": ic or None, "net": layers("net")})
             else:
                 bn = None
                 if p + "bn.mean" in flat:
@@ -512,7 +543,7 @@ def _linear_init(rng, out_f, in_f):
 
 
 def make_synthetic_model(kind, D, C, K, h, seed=1, depth=1, act="tanh", coupling="affine", batch_norm=False,
-                         rho_init="decreasing", toy_base=False, init_rows=4096, x_init=None):
+                         rho_init="decreasing", toy_base=False, init_rows=4096, x_init=None, invconv=False):
     """Random-init model of the named architecture with the same init *distributions* as the reference
     (nn.Linear default init; ActNorm initialised from data; permutation = shuffled reversed arange;
     rho per models/boosted_flow.py:32-39).  Used for full-size parity and the benchmark; NOT bit-identical to a
@@ -543,6 +574,10 @@ def make_synthetic_model(kind, D, C, K, h, seed=1, depth=1, act="tanh", coupling
                 perm = np.arange(D - 1, -1, -1)[rng.permutation(D)].astype(np.int64)
                 bias, logs = actnorm_init(z)
                 st = {"an_bias": bias, "an_logs": logs, "perm": perm, "net": net}
+                if invconv:     # plain (not LU-decomposed) weight: a random rotation (upstream's init) times mild column scales
+                    q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+                    st["ic"] = {"weight": (q * np.exp(0.1 * rng.standard_normal(D))).astype(np.float32)}
+                    st["perm"] = None
                 z, ldj = glow_step(z, ldj, st, coupling, act)
             else:
                 flipped = ((k + c) % 2) > 0
@@ -551,6 +586,11 @@ def make_synthetic_model(kind, D, C, K, h, seed=1, depth=1, act="tanh", coupling
                 dims = [i_d] + [h] * (nlin - 1) + [o_d]
                 t = [_linear_init(rng, dims[i + 1], dims[i]) for i in range(nlin)]
                 s = [_linear_init(rng, dims[i + 1], dims[i]) for i in range(nlin)]
+                if act == "residual":      # a block's second Linear starts at uniform(-1e-3, 1e-3) (models/layers.py:262-264)
+                    for net_ in (t, s):
+                        for i in range(2, nlin - 1, 2):
+                            net_[i] = (rng.uniform(-1e-3, 1e-3, net_[i][0].shape).astype(np.float32),
+                                       rng.uniform(-1e-3, 1e-3, net_[i][1].shape).astype(np.float32))
                 bn = None
                 if batch_norm and k < K - 1:
                     bn = {"log_gamma": (0.1 * rng.standard_normal(D)).astype(np.float32),

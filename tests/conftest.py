@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["glow_d43", "glow_d6_additive_relu", "realnvp_d6_bn", "realnvp_d5_mixed", "glow_d43_h256", "realnvp_d6_h128_bn",
                 "toy_d2", "glow_d43_h512", "glow_d43_h128_depth2"]
 # ResidualNet s / t networks: served by the exact fp32 kernel only (the f16 tensor-core modes reject them)
-FP32_ONLY_CASES = ["realnvp_d6_residual", "realnvp_d5_residual2_bn"]
+FP32_ONLY_CASES = ["realnvp_d6_residual", "realnvp_d5_residual2_bn", "glow_d6_invconv", "glow_d43_invconv_plain"]
 ALL_CASES = GOLDEN_CASES + FP32_ONLY_CASES
 
 

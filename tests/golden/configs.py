@@ -19,6 +19,11 @@ CONFIGS = {
     "realnvp_d6_residual": (dict(kind="realnvp", D=6, C=2, K=3, h=64, coupling_network="residual"), 10, 140, False),
     "realnvp_d5_residual2_bn": (dict(kind="realnvp", D=5, C=2, K=2, h=64, coupling_network="residual", coupling_network_depth=2,
                                      batch_norm=True), 11, 120, False),
+    # Glow with the invertible 1x1 convolution as the permutation (models/glow.py:275-278, models/layers.py:722-796; LU-decomposed
+    # and plain).  (Glow + ResidualNet cannot be built upstream: models/glow.py:294 names ResidualNet without importing it.)  Upstream's InvertibleConv1x1.forward unpacks a
+    # 4-D shape and crashes on feature vectors: make_golden.py feeds it [B, D, 1, 1] views (the fixture script only).
+    "glow_d6_invconv": (dict(kind="glow", D=6, C=2, K=3, h=64, flow_permutation="invconv"), 13, 150, False),
+    "glow_d43_invconv_plain": (dict(kind="glow", D=43, C=2, K=2, h=64, flow_permutation="invconv", LU_decomposed=False), 14, 140, False),
 }
 # fixtures whose initial state_dict is stored as per-tensor SHA-1 digests instead of values (file size)
 STATE0_DIGEST_ONLY = {"glow_d43_h512"}

@@ -34,6 +34,24 @@ for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.col
         sys.modules[name] = m
 
 from models.boosted_flow import BoostedFlow as RefBoostedFlow  # noqa: E402
+import models.layers as ref_layers  # noqa: E402
+
+# Upstream's InvertibleConv1x1 is written for images: get_weight unpacks `b, c, h, w = sample.shape` (models/layers.py:751) and
+# F.conv2d needs 4-D input, so flow_permutation='invconv' crashes on the tabular path.  In THIS SCRIPT ONLY a feature vector is
+# handed to the unmodified module as the 1 x 1 image it is; parameters, weight formula and log-det are upstream's own.
+_ref_invconv_forward = ref_layers.InvertibleConv1x1.forward
+
+
+def _invconv_forward_1d(self, sample, logdet=None, reverse=False):
+    if sample.dim() == 2:
+        if self.LU_decomposed and self.l_mask.dtype != sample.dtype:     # plain attributes: .double() does not convert them, and
+            self.l_mask, self.eye = self.l_mask.to(sample.dtype), self.eye.to(sample.dtype)   # get_weight's in-place `u +=` needs one dtype
+        z, ld = _ref_invconv_forward(self, sample[:, :, None, None], logdet, reverse)
+        return z[:, :, 0, 0], ld
+    return _ref_invconv_forward(self, sample, logdet, reverse)
+
+
+ref_layers.InvertibleConv1x1.forward = _invconv_forward_1d
 import density_experiment as ref_density  # noqa: E402
 from utils.distributions import log_normal_standard  # noqa: E402
 
@@ -113,10 +131,15 @@ def build_case(name):
             for k in range(args.num_flows):
                 src = model.flows[c].flow.layers[k]
                 dst = m64.flows[c].flow.layers[k]
+                dst.actnorm.inited = True
+                if hasattr(src, "invconv"):
+                    # FlowStep.flow_permutation is a lambda closing over the ORIGINAL step (models/glow.py:277-278); deepcopy keeps
+                    # the function object, so the copy would run the fp32 convolution: rebind it to the copy's own module
+                    dst.flow_permutation = lambda z, logdet, rev, _s=dst: _s.invconv(z, logdet, rev)
+                    continue
                 psrc = src.shuffle if hasattr(src, "shuffle") else src.reverse
                 pdst = dst.shuffle if hasattr(dst, "shuffle") else dst.reverse
                 pdst.indices = psrc.indices.clone()
-                dst.actnorm.inited = True
     with torch.no_grad():
         z64, ldj64, lq64 = ref_forward_all(m64, x.double(), toy_base)
 

@@ -42,7 +42,11 @@ def load_into(model, md):
                     step.actnorm.bias.copy_(t(st["an_bias"]).view(1, -1))
                     step.actnorm.logs.copy_(t(st["an_logs"]).view(1, -1))
                     step.actnorm.inited = True
-                    step.permutation.set_indices(t(st["perm"]))
+                    if st.get("ic") is not None:
+                        for n_, v in st["ic"].items():
+                            getattr(step.invconv, n_).copy_(t(v))
+                    else:
+                        step.permutation.set_indices(t(st["perm"]))
                     nets = [(step.block, st["net"])]
                 else:
                     nets = [(step[0], st["t"]), (step[1], st["s"])]
@@ -58,7 +62,10 @@ def load_into(model, md):
 
 def build_model(md, device="cpu", gemm_mode="fp32", **kw):
     import gbnf_b200
-    perm_kind = "shuffle"
+    ic = md["components"][0]["steps"][0].get("ic") if md["kind"] == "glow" else None
+    perm_kind = "invconv" if ic is not None else "shuffle"
+    if ic is not None:
+        kw.setdefault("LU_decomposed", "weight" not in ic)
     a = args_for(md, device, flow_permutation=perm_kind, **kw)
     torch.manual_seed(0)
     m = gbnf_b200.BoostedFlow(a, gemm_mode=gemm_mode)

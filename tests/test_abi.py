@@ -31,12 +31,12 @@ def test_header_symbols_exported_and_bound():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True).stdout
     for n in names:
         assert re.search(rf"\bT {n}\b", out), n
-    assert lib.gbnf_abi_version() == 1
+    assert lib.gbnf_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Config) == 12 * 4
-    assert C.sizeof(_lib.StepParams) == (7 + 2 * 2 * _lib.GBNF_MAX_LAYERS) * 8
+    assert C.sizeof(_lib.StepParams) == (7 + 2 * 2 * _lib.GBNF_MAX_LAYERS + 3) * 8      # + invconv_w / _winv / _logdet (ABI 2)
     assert C.sizeof(_lib.ComponentParams) == 16
     assert C.sizeof(_lib.Info) == 6 * 4 + 2 * 8 + 2 * 4
 
@@ -61,7 +61,8 @@ def test_argument_validation_without_gpu():
     h = C.c_void_p()
     assert lib.gbnf_create(C.byref(h), None) == -1
     for bad in (dict(kind=7), dict(D=1), dict(D=4000), dict(C=0), dict(depth=9), dict(act=5), dict(gemm_mode=3),
-                dict(kind=1, act=2)):
+                dict(kind=1, act=2), dict(kind=1, act=3), dict(kind=0, act=3, depth=3), dict(kind=0, act=3, gemm_mode=1),
+                dict(kind=0, glow_invconv=1), dict(kind=1, glow_invconv=1, gemm_mode=2), dict(kind=1, glow_invconv=2)):
         kw = dict(kind=1, D=43, h=512, K=5, C=8, depth=1)
         kw.update(bad)
         assert lib.gbnf_create(C.byref(h), C.byref(_lib.Config(**kw))) == -1, bad
