@@ -148,9 +148,13 @@ class BoostedFlow(nn.Module):
     @torch.no_grad()
     def _fused_backward_ok(self, x):
         a = self.args
-        return (self.fused_backward and x.is_cuda and x.dtype == torch.float32 and self.component_type == "glow"
-                and a.coupling_network_depth == 1 and a.h_size <= 512 and self.z_size <= 64 and a.num_flows <= 32
-                and a.coupling_network in ("tanh", "relu") and getattr(a, "flow_permutation", "shuffle") != "invconv")
+        if not (self.fused_backward and x.is_cuda and x.dtype == torch.float32 and a.coupling_network_depth == 1
+                and a.h_size <= 512 and self.z_size <= 64 and a.num_flows <= 32):
+            return False
+        if self.component_type == "glow":
+            return a.coupling_network in ("tanh", "relu") and getattr(a, "flow_permutation", "shuffle") != "invconv"
+        # RealNVP: train-mode BatchNorm couples the rows of a batch -> those configurations stay on the caller's autograd
+        return a.coupling_network in ("tanh", "relu", "mixed") and not getattr(a, "batch_norm", False)
 
     def _component_backward(self, c, x, dz, dldj):
         """Gradients of component c's parameters for upstream (dz, dldj): {id(param): grad} (gbnf_component_backward)."""
@@ -174,14 +178,16 @@ class BoostedFlow(nn.Module):
 
         for k, (d, step) in enumerate(zip(steps, self.flows[c].steps())):
             sp, sg = parr[k], garr[k]
-            sp.an_bias, sp.an_logs = dev(d["an_bias"].reshape(-1)), dev(d["an_logs"].reshape(-1))
-            sp.perm = dev(d["perm"], torch.int64)
-            sg.an_bias, sg.an_logs = grad_of(step.actnorm.bias), grad_of(step.actnorm.logs)
-            for l, lin in enumerate(d["nets"][0]):
-                sp.W[0][l], sp.b[0][l] = dev(lin.weight), dev(lin.bias)
-                sg.W[0][l], sg.b[0][l] = grad_of(lin.weight), grad_of(lin.bias)
+            if "an_bias" in d:
+                sp.an_bias, sp.an_logs = dev(d["an_bias"].reshape(-1)), dev(d["an_logs"].reshape(-1))
+                sp.perm = dev(d["perm"], torch.int64)
+                sg.an_bias, sg.an_logs = grad_of(step.actnorm.bias), grad_of(step.actnorm.logs)
+            for n, lins in enumerate(d["nets"]):          # Glow: the block; RealNVP: t_net, s_net
+                for l, lin in enumerate(lins):
+                    sp.W[n][l], sp.b[n][l] = dev(lin.weight), dev(lin.bias)
+                    sg.W[n][l], sg.b[n][l] = grad_of(lin.weight), grad_of(lin.bias)
         cp = _lib.ComponentParams()
-        cp.flip_init, cp.n_steps = 0, len(steps)
+        cp.flip_init, cp.n_steps = getattr(self.flows[c], "flip_init", 0), len(steps)
         cp.steps = C.cast(parr, C.POINTER(_lib.StepParams))
         _lib.check(lib.gbnf_component_backward(h, c, C.byref(cp), _ptr(x), x.shape[0], _ptr(dz), _ptr(dldj),
                                                C.cast(garr, C.POINTER(_lib.StepGrads)), None, _stream(device)))

@@ -113,7 +113,8 @@ struct gbnf_ctx {
   float* tr_w = nullptr;         // fp32 copies of its weights in both layouts + padded biases + 1024 zeros
   long long tr_w_floats = 0;
   float* tr_scratch = nullptr;   // per-step activations / d pre-activations [B][...]
-  long long tr_rows = 0;
+  long long tr_rows = 0, tr_per_row = 0;
+  int tr_njobs = 0;
   TrainStep* tr_steps_d = nullptr;
   TrainPackJob* tr_pack_d = nullptr;
   WgradJob* tr_jobs_d = nullptr;
@@ -734,90 +735,127 @@ int gbnf_component_backward(gbnf_handle h, int32_t c, const gbnf_component_param
   if (!h || !p || !p->steps || !grads || !d_x || !d_dz || !d_dldj) return fail(GBNF_ERR_INVALID, "null argument");
   if (c < 0 || c >= h->cfg.C || p->n_steps != h->cfg.K) return fail(GBNF_ERR_INVALID, "bad component index / n_steps");
   const gbnf_config& cf = h->cfg;
-  if (cf.kind != GBNF_KIND_GLOW || cf.glow_invconv || cf.depth != 1 || cf.act == GBNF_ACT_MIXED || cf.act == GBNF_ACT_RESIDUAL || cf.h > 512 || cf.D > 64 || cf.K > kTrMaxK)
-    return fail(GBNF_ERR_INVALID, "fused backward: Glow components with coupling_network_depth 1, h <= 512, D <= 64 (others train through "
-                                  "the caller's autograd)");
+  const bool glow = cf.kind == GBNF_KIND_GLOW;
+  if (cf.glow_invconv || cf.depth != 1 || cf.act == GBNF_ACT_RESIDUAL || (glow && cf.act == GBNF_ACT_MIXED) || cf.h > 512 || cf.D > 64 ||
+      cf.K > kTrMaxK)
+    return fail(GBNF_ERR_INVALID, "fused backward: Glow (with a permutation) or RealNVP (without BatchNorm) components with "
+                                  "coupling_network_depth 1, tanh / relu (RealNVP: or mixed) networks, h <= 512, D <= 64 (others train "
+                                  "through the caller's autograd)");
+  if (!glow && p->flip_init != c) return fail(GBNF_ERR_INVALID, "RealNVP component c must have flip_init == c (models/boosted_flow.py:46)");
   if (B <= 0) return fail(GBNF_ERR_INVALID, "empty batch");
   ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
-  const int K = cf.K, D = cf.D, h0 = D / 2, h1 = D - h0;
-  const int n3 = (cf.coupling == GBNF_COUPLING_AFFINE) ? 2 * h1 : h1;
+  const int K = cf.K, D = cf.D, hD0 = D / 2, hD1 = D - hD0;
+  const int nnets = glow ? 1 : 2;
   const int hp = round_up(cf.h, 64);
-  const int Kd[3] = {h0, cf.h, cf.h}, Nn[3] = {cf.h, cf.h, n3};
-  int Kp[3], Np[3], NKp[3], KNp[3];
-  long long per_step = 0;
-  for (int l = 0; l < 3; ++l) {
-    Kp[l] = round_up(Kd[l], kF32KT); Np[l] = round_up(Nn[l], kF32NT);
-    NKp[l] = round_up(Nn[l], kF32KT); KNp[l] = round_up(Kd[l], kF32NT);
-    per_step += (long long)Kp[l] * Np[l] + (long long)NKp[l] * KNp[l] + Np[l];
+  // per-step geometry: RealNVP steps alternate |z1| / |z2| when D is odd (flipped iff (k + c) is odd, models/realnvp.py:37-43)
+  struct Geo { int in_dim, out_dim, Kd[3], Nn[3], Kp[3], Np[3], NKp[3], KNp[3]; long long wfloats; };
+  std::vector<Geo> geo(K);
+  long long need_w = 1024;
+  int ldz1 = 0;
+  for (int k = 0; k < K; ++k) {
+    Geo& g = geo[k];
+    const bool flipped = !glow && (((k + c) % 2) > 0);
+    g.in_dim = flipped ? hD1 : hD0; g.out_dim = flipped ? hD0 : hD1;
+    const int n3 = glow ? ((cf.coupling == GBNF_COUPLING_AFFINE) ? 2 * g.out_dim : g.out_dim) : g.out_dim;
+    const int Kd[3] = {g.in_dim, cf.h, cf.h}, Nn[3] = {cf.h, cf.h, n3};
+    g.wfloats = 0;
+    for (int l = 0; l < 3; ++l) {
+      g.Kd[l] = Kd[l]; g.Nn[l] = Nn[l];
+      g.Kp[l] = round_up(Kd[l], kF32KT); g.Np[l] = round_up(Nn[l], kF32NT);
+      g.NKp[l] = round_up(Nn[l], kF32KT); g.KNp[l] = round_up(Kd[l], kF32NT);
+      g.wfloats += (long long)g.Kp[l] * g.Np[l] + (long long)g.NKp[l] * g.KNp[l] + g.Np[l];
+    }
+    g.wfloats *= nnets;
+    need_w += g.wfloats;
+    ldz1 = std::max(ldz1, g.Kp[0]);
   }
-  const long long need_w = per_step * K + 1024;
   if (need_w > h->tr_w_floats) {
     if (h->tr_w) cudaFree(h->tr_w);
     h->tr_w = nullptr; h->tr_w_floats = 0;
     CUDA_TRY_H(h, cudaMalloc(&h->tr_w, need_w * sizeof(float)));
     h->tr_w_floats = need_w;
   }
-  const int ldz1 = Kp[0];
-  const long long per_row = (long long)ldz1 + 4LL * hp + 64;
-  if (B > h->tr_rows) {
+  const long long per_row = (long long)ldz1 + nnets * (4LL * hp + 64);
+  if (B > h->tr_rows || per_row > h->tr_per_row) {
     if (h->tr_scratch) cudaFree(h->tr_scratch);
     h->tr_scratch = nullptr; h->tr_rows = 0;
-    const long long rows = std::max<long long>(B, 1024);
+    const long long rows = std::max<long long>(std::max<long long>(B, h->tr_rows), 1024);
     CUDA_TRY_H(h, cudaMalloc(&h->tr_scratch, (size_t)rows * per_row * K * sizeof(float)));
-    h->tr_rows = rows;
+    h->tr_rows = rows; h->tr_per_row = per_row;
   }
-  if (!h->tr_steps_d) {
+  const int njobs = K * nnets * 3;
+  if (!h->tr_steps_d || njobs > h->tr_njobs) {
+    if (h->tr_steps_d) { cudaFree(h->tr_steps_d); cudaFree(h->tr_pack_d); cudaFree(h->tr_jobs_d); }
     CUDA_TRY_H(h, cudaMalloc(&h->tr_steps_d, (size_t)K * sizeof(TrainStep)));
-    CUDA_TRY_H(h, cudaMalloc(&h->tr_pack_d, (size_t)K * 3 * sizeof(TrainPackJob)));
-    CUDA_TRY_H(h, cudaMalloc(&h->tr_jobs_d, (size_t)K * 3 * sizeof(WgradJob)));
+    CUDA_TRY_H(h, cudaMalloc(&h->tr_pack_d, (size_t)njobs * sizeof(TrainPackJob)));
+    CUDA_TRY_H(h, cudaMalloc(&h->tr_jobs_d, (size_t)njobs * sizeof(WgradJob)));
+    h->tr_njobs = njobs;
   }
-  h->tr_steps_h.assign(K, TrainStep{}); h->tr_pack_h.assign((size_t)K * 3, TrainPackJob{}); h->tr_jobs_h.assign((size_t)K * 3, WgradJob{});
-  float* zeros = h->tr_w + per_step * K;
-  int tile0 = 0;
+  h->tr_steps_h.assign(K, TrainStep{}); h->tr_pack_h.assign((size_t)njobs, TrainPackJob{}); h->tr_jobs_h.assign((size_t)njobs, WgradJob{});
+  float* w = h->tr_w;
+  float* zeros = h->tr_w + (need_w - 1024);
+  int tile0 = 0, job = 0;
   for (int k = 0; k < K; ++k) {
     const gbnf_step_params& sp = p->steps[k];
     const gbnf_step_grads& sg = grads[k];
-    if (!sp.an_bias || !sp.an_logs || !sp.perm || !sg.an_bias || !sg.an_logs) return fail(GBNF_ERR_INVALID, "glow step needs ActNorm / perm / gradient pointers");
+    const Geo& g = geo[k];
     TrainStep& ts = h->tr_steps_h[k];
-    ts.an_bias = sp.an_bias; ts.an_logs = sp.an_logs; ts.perm = (const long long*)sp.perm;
-    ts.g_bias = sg.an_bias; ts.g_logs = sg.an_logs;
-    float* w = h->tr_w + per_step * k;
-    float* sc = h->tr_scratch + (size_t)k * h->tr_rows * per_row;
-    ts.z1 = sc; ts.h1 = ts.z1 + h->tr_rows * ldz1; ts.h2 = ts.h1 + h->tr_rows * hp; ts.d1 = ts.h2 + h->tr_rows * hp;
-    ts.d2 = ts.d1 + h->tr_rows * hp; ts.d3 = ts.d2 + h->tr_rows * hp;
-    for (int l = 0; l < 3; ++l) {
-      if (!sp.W[0][l] || !sp.b[0][l] || !sg.W[0][l] || !sg.b[0][l]) return fail(GBNF_ERR_INVALID, "missing Linear weight / bias / gradient pointer");
-      TrainPackJob& pj = h->tr_pack_h[(size_t)k * 3 + l];
-      pj.W = sp.W[0][l]; pj.b = sp.b[0][l]; pj.N = Nn[l]; pj.Kd = Kd[l]; pj.Kp = Kp[l]; pj.Np = Np[l]; pj.NKp = NKp[l]; pj.KNp = KNp[l];
-      pj.Wt = w; w += (long long)Kp[l] * Np[l];
-      pj.Wn = w; w += (long long)NKp[l] * KNp[l];
-      pj.bp = w; w += Np[l];
-      ts.Wt[l] = pj.Wt; ts.Wn[l] = pj.Wn; ts.b[l] = pj.bp; ts.Kp[l] = Kp[l]; ts.Np[l] = Np[l]; ts.NKp[l] = NKp[l]; ts.KNp[l] = KNp[l];
-      WgradJob& wj = h->tr_jobs_h[(size_t)k * 3 + l];
-      wj.dact = (l == 0) ? ts.d1 : (l == 1) ? ts.d2 : ts.d3;  wj.ld_d = (l == 2) ? 64 : hp;
-      wj.in = (l == 0) ? ts.z1 : (l == 1) ? ts.h1 : ts.h2;     wj.ld_i = (l == 0) ? ldz1 : hp;
-      wj.dW = sg.W[0][l]; wj.db = sg.b[0][l]; wj.N = Nn[l]; wj.Kd = Kd[l];
-      wj.tiles_n = (Nn[l] + 63) / 64; wj.tiles_k = (Kd[l] + 63) / 64; wj.tile0 = tile0;
-      tile0 += wj.tiles_n * wj.tiles_k;
+    if (glow) {
+      if (!sp.an_bias || !sp.an_logs || !sp.perm || !sg.an_bias || !sg.an_logs) return fail(GBNF_ERR_INVALID, "glow step needs ActNorm / perm / gradient pointers");
+      ts.an_bias = sp.an_bias; ts.an_logs = sp.an_logs; ts.perm = (const long long*)sp.perm;
+      ts.g_bias = sg.an_bias; ts.g_logs = sg.an_logs;
+    } else if (sp.bn_log_gamma || sp.bn_beta || sp.bn_mean || sp.bn_var) {
+      return fail(GBNF_ERR_INVALID, "fused backward: RealNVP steps with BatchNorm train through the caller's autograd (train-mode batch "
+                                    "statistics couple the rows of a batch)");
     }
-    CUDA_TRY_H(h, cudaMemsetAsync(sg.an_bias, 0, (size_t)D * sizeof(float), st));
-    CUDA_TRY_H(h, cudaMemsetAsync(sg.an_logs, 0, (size_t)D * sizeof(float), st));
+    ts.flipped = (!glow && (((k + c) % 2) > 0)) ? 1 : 0; ts.in_dim = g.in_dim; ts.out_dim = g.out_dim;
+    float* sc = h->tr_scratch + (size_t)k * h->tr_rows * per_row;
+    ts.z1 = sc; sc += h->tr_rows * ldz1;
+    for (int l = 0; l < 3; ++l) { ts.Kp[l] = g.Kp[l]; ts.Np[l] = g.Np[l]; ts.NKp[l] = g.NKp[l]; ts.KNp[l] = g.KNp[l]; }
+    // note: z1 rows are stored with stride Kp[0] of THIS step (<= ldz1)
+    for (int net = 0; net < nnets; ++net) {
+      ts.h1[net] = sc; sc += h->tr_rows * hp;
+      ts.h2[net] = sc; sc += h->tr_rows * hp;
+      ts.d1[net] = sc; sc += h->tr_rows * hp;
+      ts.d2[net] = sc; sc += h->tr_rows * hp;
+      ts.d3[net] = sc; sc += h->tr_rows * 64;
+      for (int l = 0; l < 3; ++l) {
+        if (!sp.W[net][l] || !sp.b[net][l] || !sg.W[net][l] || !sg.b[net][l]) return fail(GBNF_ERR_INVALID, "missing Linear weight / bias / gradient pointer");
+        TrainPackJob& pj = h->tr_pack_h[(size_t)job];
+        pj.W = sp.W[net][l]; pj.b = sp.b[net][l]; pj.N = g.Nn[l]; pj.Kd = g.Kd[l]; pj.Kp = g.Kp[l]; pj.Np = g.Np[l]; pj.NKp = g.NKp[l]; pj.KNp = g.KNp[l];
+        pj.Wt = w; w += (long long)g.Kp[l] * g.Np[l];
+        pj.Wn = w; w += (long long)g.NKp[l] * g.KNp[l];
+        pj.bp = w; w += g.Np[l];
+        ts.Wt[net][l] = pj.Wt; ts.Wn[net][l] = pj.Wn; ts.b[net][l] = pj.bp;
+        WgradJob& wj = h->tr_jobs_h[(size_t)job];
+        wj.dact = (l == 0) ? ts.d1[net] : (l == 1) ? ts.d2[net] : ts.d3[net];  wj.ld_d = (l == 2) ? g.Np[2] : hp;
+        wj.in = (l == 0) ? ts.z1 : (l == 1) ? ts.h1[net] : ts.h2[net];          wj.ld_i = (l == 0) ? g.Kp[0] : hp;
+        wj.dW = sg.W[net][l]; wj.db = sg.b[net][l]; wj.N = g.Nn[l]; wj.Kd = g.Kd[l];
+        wj.tiles_n = (g.Nn[l] + 63) / 64; wj.tiles_k = (g.Kd[l] + 63) / 64; wj.tile0 = tile0;
+        tile0 += wj.tiles_n * wj.tiles_k;
+        ++job;
+      }
+    }
+    if (glow) {
+      CUDA_TRY_H(h, cudaMemsetAsync(sg.an_bias, 0, (size_t)D * sizeof(float), st));
+      CUDA_TRY_H(h, cudaMemsetAsync(sg.an_logs, 0, (size_t)D * sizeof(float), st));
+    }
   }
   CUDA_TRY_H(h, cudaMemcpyAsync(h->tr_steps_d, h->tr_steps_h.data(), (size_t)K * sizeof(TrainStep), cudaMemcpyHostToDevice, st));
-  CUDA_TRY_H(h, cudaMemcpyAsync(h->tr_pack_d, h->tr_pack_h.data(), (size_t)K * 3 * sizeof(TrainPackJob), cudaMemcpyHostToDevice, st));
-  CUDA_TRY_H(h, cudaMemcpyAsync(h->tr_jobs_d, h->tr_jobs_h.data(), (size_t)K * 3 * sizeof(WgradJob), cudaMemcpyHostToDevice, st));
+  CUDA_TRY_H(h, cudaMemcpyAsync(h->tr_pack_d, h->tr_pack_h.data(), (size_t)njobs * sizeof(TrainPackJob), cudaMemcpyHostToDevice, st));
+  CUDA_TRY_H(h, cudaMemcpyAsync(h->tr_jobs_d, h->tr_jobs_h.data(), (size_t)njobs * sizeof(WgradJob), cudaMemcpyHostToDevice, st));
   CUDA_TRY_H(h, cudaMemsetAsync(zeros, 0, 1024 * sizeof(float), st));
-  train_pack_kernel<<<dim3(32, K * 3), 256, 0, st>>>(h->tr_pack_d);
+  train_pack_kernel<<<dim3(32, njobs), 256, 0, st>>>(h->tr_pack_d);
   TrainArgs ta{};
   ta.x = d_x; ta.B = B; ta.dz = d_dz; ta.dldj = d_dldj; ta.steps = h->tr_steps_d; ta.K = K; ta.D = D; ta.h = cf.h; ta.hp = hp;
-  ta.act = cf.act; ta.coupling = cf.coupling; ta.in_dim = h0; ta.out_dim = h1; ta.n3 = n3; ta.ld = hp + 4; ta.zeros = zeros; ta.dx = d_dx_opt;
-  const size_t smem = ((size_t)(((K + 1) * kTrR * D + 3) & ~3) + (size_t)K * kTrR * 64 + 3ull * kTrR * ta.ld + 2ull * kF32KT * kF32NT +
+  ta.act = cf.act; ta.coupling = cf.coupling; ta.kind = cf.kind; ta.nnets = nnets; ta.ld = std::max(hp, ldz1) + 4; ta.zeros = zeros; ta.dx = d_dx_opt;
+  const size_t smem = ((size_t)(((K + 1) * kTrR * D + 3) & ~3) + (size_t)K * 2 * kTrR * 64 + 3ull * kTrR * ta.ld + 2ull * kF32KT * kF32NT +
                        2ull * ((kTrR * D + 3) & ~3)) * sizeof(float);
   if (smem > 227 * 1024) return fail(GBNF_ERR_INVALID, "fused backward: shared-memory history too large (K x D)");
   CUDA_TRY_H(h, cudaFuncSetAttribute(train_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   train_bwd_rows_kernel<<<(unsigned)((B + kTrR - 1) / kTrR), kF32Threads, smem, st>>>(ta);
-  train_wgrad_kernel<<<tile0, 256, 0, st>>>(h->tr_jobs_d, K * 3, B);
+  train_wgrad_kernel<<<tile0, 256, 0, st>>>(h->tr_jobs_d, njobs, B);
   h->launches += 3;
   CUDA_TRY_H(h, cudaGetLastError());
   return GBNF_OK;

@@ -12,8 +12,12 @@
 //            (step, layer): 64 x 64 output tiles over ALL rows, written straight into the caller's gradient tensors
 //            (deterministic: no atomics on the weight gradients).
 // fp32 CUDA-core arithmetic throughout (reference-class numerics: the gate is 1e-4 on the gradients).
-// Model: Glow step = ActNorm1d -> Permute1d -> affine / additive coupling with one MLP of depth 1 (models/glow.py:317-342,
-// models/layers.py:208-243,488-518,661-668), in the reference's own (logical) column order.
+// Models, in the reference's own (logical) column order, coupling networks of depth 1:
+//   Glow step    = ActNorm1d -> Permute1d -> affine / additive coupling with ONE MLP (models/glow.py:317-342,
+//                  models/layers.py:208-243,488-518,661-668);
+//   RealNVP step = [z1 | z2] split (swapped when the step is flipped) -> z2' = t(z1) + z2 exp(s(z1)) with TWO MLPs, output
+//                  [z1, z2'] (models/transformations.py:560-579, models/realnvp.py:35-76); steps WITHOUT BatchNorm only
+//                  (train-mode BatchNorm couples the rows of a batch: those configurations train through autograd).
 #pragma once
 #include "coupling_fp32.cuh"
 
@@ -23,22 +27,23 @@ constexpr int kTrR = 16;             // rows per CTA of phase A
 constexpr int kTrMaxK = 32;          // coupling steps per component supported by the shared-memory history
 
 struct TrainStep {                   // one coupling step of the component under training (device pointers)
-  const float* an_bias; const float* an_logs; const long long* perm;       // raw reference tensors
-  const float* Wt[3];                // forward layout  Wt[Kp][Np]   (k-major, n contiguous, zero padded)
-  const float* Wn[3];                // backward layout Wn[NKp][KNp] (nn.Linear rows = n, k contiguous, zero padded)
-  const float* b[3];                 // biases padded to Np
+  const float* an_bias; const float* an_logs; const long long* perm;       // Glow: raw reference tensors; RealNVP: null
+  int flipped, in_dim, out_dim, pad_;                                      // RealNVP: (k + flip_init) odd; |z1|, |z2| of this step
+  const float* Wt[2][3];             // forward layout  Wt[Kp][Np]   (k-major, n contiguous, zero padded); net 0 = glow block / t, 1 = s
+  const float* Wn[2][3];             // backward layout Wn[NKp][KNp] (nn.Linear rows = n, k contiguous, zero padded)
+  const float* b[2][3];              // biases padded to Np
   int Kp[3], Np[3];                  // forward padding (Kp % 32 == 0, Np % 64 == 0)
   int NKp[3], KNp[3];                // backward padding: rows (n) to a multiple of 32, columns (k) to a multiple of 64
   float* g_bias; float* g_logs;      // ActNorm gradients [D] (accumulated with atomics; zeroed by the host)
   // scratch (per step, [B][ld]): activations and d pre-activations for phase B
-  float* z1; float* h1; float* h2; float* d1; float* d2; float* d3;
+  float* z1; float* h1[2]; float* h2[2]; float* d1[2]; float* d2[2]; float* d3[2];
 };
 
 struct TrainArgs {
   const float* x; long long B;
   const float* dz; const float* dldj;          // upstream gradients dL/dz [B, D], dL/dldj [B]
   const TrainStep* steps; int K;
-  int D, h, hp, act, coupling, in_dim, out_dim, n3;   // n3 = last layer width (2 out_dim for affine)
+  int D, h, hp, act, coupling, kind, nnets;
   int ld;                                      // row stride of the shared activation buffers
   const float* zeros;                          // >= 1024 zero floats (bias of the data-gradient GEMMs)
   float* dx;                                   // optional dL/dx [B, D]
@@ -49,14 +54,29 @@ __device__ __forceinline__ float act_grad_from_output(float hval) {
   return ACT == 1 ? (1.f - hval * hval) : (hval > 0.f ? 1.f : 0.f);     // tanh' = 1 - tanh^2 ; relu' from its output
 }
 
-// Dynamic smem: zh[(K+1)][R][D] | oh[K][R][64] | act0[R][ld] | act1[R][ld] | act2[R][ld] | Ws[2][32][64] | dzb[R][D] | tmp[R][D]
+// column of the step's INPUT that feeds position j of the coupling order [z1 | z2]
+__device__ __forceinline__ int train_src_col(const TrainStep& s, int kind, int j, int h0) {
+  if (kind == GBNF_KIND_GLOW) return (int)s.perm[j];
+  if (!s.flipped) return j;
+  return (j < s.in_dim) ? h0 + j : j - s.in_dim;                 // flipped: z1 = x[:, h0:], z2 = x[:, :h0]
+}
+template <int R>
+__device__ __forceinline__ void train_gemm(int act_kind, const float* in, float* out, int ld, const float* Wt, const float* b, int Kp, int Np,
+                                           float* Ws) {
+  if (act_kind == 2)      gemm_layer_fp32<R, 2>(in, out, ld, Wt, b, Kp, Np, Ws);
+  else if (act_kind == 1) gemm_layer_fp32<R, 1>(in, out, ld, Wt, b, Kp, Np, Ws);
+  else                    gemm_layer_fp32<R, 0>(in, out, ld, Wt, b, Kp, Np, Ws);
+}
+
+// Dynamic smem: zh[(K+1)][R][D] | oh[K][2][R][64] | act0[R][ld] | act1[R][ld] | act2[R][ld] | Ws[2][32][64] | dzb[R][D] | tmp[R][D]
 __global__ void __launch_bounds__(kF32Threads, 1) train_bwd_rows_kernel(TrainArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int R = kTrR;
-  const int D = a.D, K = a.K, ld = a.ld, h0 = a.in_dim, h1d = a.out_dim;
+  const int D = a.D, K = a.K, ld = a.ld, hD0 = a.D / 2;
+  const bool glow = a.kind == GBNF_KIND_GLOW;
   float* zh = reinterpret_cast<float*>(smem_raw);
   float* oh = zh + (((K + 1) * R * D + 3) & ~3);
-  float* act0 = oh + K * R * 64;
+  float* act0 = oh + K * 2 * R * 64;
   float* act1 = act0 + R * ld;
   float* act2 = act1 + R * ld;
   float* Ws = act2 + R * ld;
@@ -65,6 +85,7 @@ __global__ void __launch_bounds__(kF32Threads, 1) train_bwd_rows_kernel(TrainArg
   const int tid = threadIdx.x;
   const long long row0 = (long long)blockIdx.x * R;
   const int hp = a.hp;
+  auto act_of = [&](int net) { return (a.act == GBNF_ACT_TANH) ? 1 : (a.act == GBNF_ACT_RELU) ? 2 : (net == 0 ? 2 : 1); };   // mixed: t ReLU, s tanh
 
   // ---------------- forward sweep ----------------
   for (int i = tid; i < R * D; i += kF32Threads) {
@@ -75,45 +96,52 @@ __global__ void __launch_bounds__(kF32Threads, 1) train_bwd_rows_kernel(TrainArg
   __syncthreads();
   for (int k = 0; k < K; ++k) {
     const TrainStep& s = a.steps[k];
+    const int h0 = s.in_dim;
     const float* zin = zh + k * R * D;
     float* zout = zh + (k + 1) * R * D;
-    // ActNorm + permutation: yp[:, j] = (x[:, perm[j]] + bias[perm[j]]) * exp(logs[perm[j]])   (layers.py:488-518, 661-668)
+    // coupling order [z1 | z2]: Glow yp[:, j] = (x[:, perm[j]] + bias) exp(logs) (layers.py:488-518, 661-668); RealNVP: the split
     for (int i = tid; i < R * D; i += kF32Threads) {
       const int r = i / D, j = i - r * D;
-      const int pj = (int)s.perm[j];
-      tmp[i] = (zin[r * D + pj] + s.an_bias[pj]) * expf(s.an_logs[pj]);
+      const int pj = train_src_col(s, a.kind, j, hD0);
+      tmp[i] = glow ? (zin[r * D + pj] + s.an_bias[pj]) * expf(s.an_logs[pj]) : zin[r * D + pj];
     }
     __syncthreads();
-    for (int i = tid; i < R * s.Kp[0]; i += kF32Threads) {
-      const int r = i / s.Kp[0], j = i - r * s.Kp[0];
-      const float v = (j < h0) ? tmp[r * D + j] : 0.f;
-      act0[r * ld + j] = v;
-      const long long gr = row0 + r;
-      if (gr < a.B) s.z1[gr * s.Kp[0] + j] = v;
+    for (int net = 0; net < a.nnets; ++net) {
+      for (int i = tid; i < R * s.Kp[0]; i += kF32Threads) {
+        const int r = i / s.Kp[0], j = i - r * s.Kp[0];
+        const float v = (j < h0) ? tmp[r * D + j] : 0.f;
+        act0[r * ld + j] = v;
+        const long long gr = row0 + r;
+        if (net == 0 && gr < a.B) s.z1[gr * s.Kp[0] + j] = v;
+      }
+      __syncthreads();
+      const int ak = act_of(net);
+      train_gemm<R>(ak, act0, act1, ld, s.Wt[net][0], s.b[net][0], s.Kp[0], s.Np[0], Ws);
+      train_gemm<R>(ak, act1, act2, ld, s.Wt[net][1], s.b[net][1], s.Kp[1], s.Np[1], Ws);
+      for (int i = tid; i < R * hp; i += kF32Threads) {          // h1, h2 for the backward sweep and for phase B
+        const int r = i / hp, j = i - r * hp;
+        const long long gr = row0 + r;
+        if (gr < a.B) { s.h1[net][gr * hp + j] = act1[r * ld + j]; s.h2[net][gr * hp + j] = act2[r * ld + j]; }
+      }
+      train_gemm<R>(0, act2, act0, ld, s.Wt[net][2], s.b[net][2], s.Kp[2], s.Np[2], Ws);
+      for (int i = tid; i < R * 64; i += kF32Threads) oh[((k * 2 + net) * R + (i >> 6)) * 64 + (i & 63)] = act0[(i >> 6) * ld + (i & 63)];
+      __syncthreads();
     }
-    __syncthreads();
-    if (a.act == GBNF_ACT_RELU) gemm_layer_fp32<R, 2>(act0, act1, ld, s.Wt[0], s.b[0], s.Kp[0], s.Np[0], Ws);
-    else                        gemm_layer_fp32<R, 1>(act0, act1, ld, s.Wt[0], s.b[0], s.Kp[0], s.Np[0], Ws);
-    if (a.act == GBNF_ACT_RELU) gemm_layer_fp32<R, 2>(act1, act2, ld, s.Wt[1], s.b[1], s.Kp[1], s.Np[1], Ws);
-    else                        gemm_layer_fp32<R, 1>(act1, act2, ld, s.Wt[1], s.b[1], s.Kp[1], s.Np[1], Ws);
-    for (int i = tid; i < R * hp; i += kF32Threads) {          // h1, h2 for the backward sweep and for phase B
-      const int r = i / hp, j = i - r * hp;
-      const long long gr = row0 + r;
-      if (gr < a.B) { s.h1[gr * hp + j] = act1[r * ld + j]; s.h2[gr * hp + j] = act2[r * ld + j]; }
-    }
-    gemm_layer_fp32<R, 0>(act2, act0, ld, s.Wt[2], s.b[2], s.Kp[2], s.Np[2], Ws);
-    for (int i = tid; i < R * 64; i += kF32Threads) oh[(k * R + (i >> 6)) * 64 + (i & 63)] = act0[(i >> 6) * ld + (i & 63)];
+    const float* o0 = oh + (k * 2) * R * 64;
+    const float* o1 = o0 + R * 64;
     for (int i = tid; i < R * D; i += kF32Threads) {
       const int r = i / D, j = i - r * D;
       float v = tmp[i];
       if (j >= h0) {
         const int jj = j - h0;
-        if (a.coupling == GBNF_COUPLING_AFFINE) {
-          const float shift = act0[r * ld + 2 * jj], raw = act0[r * ld + 2 * jj + 1];
+        if (!glow) {
+          v = o0[r * 64 + jj] + v * expf(o1[r * 64 + jj]);                 // transformations.py:575
+        } else if (a.coupling == GBNF_COUPLING_AFFINE) {
+          const float shift = o0[r * 64 + 2 * jj], raw = o0[r * 64 + 2 * jj + 1];
           const float sg = 1.f / (1.f + expf(-(raw + 2.f)));            // glow.py:333
           v = (v + shift) * sg;                                           // glow.py:334-335
         } else {
-          v = v + act0[r * ld + jj];                                      // glow.py:328-329
+          v = v + o0[r * 64 + jj];                                        // glow.py:328-329
         }
       }
       zout[i] = v;
@@ -129,84 +157,94 @@ __global__ void __launch_bounds__(kF32Threads, 1) train_bwd_rows_kernel(TrainArg
   __syncthreads();
   for (int k = K - 1; k >= 0; --k) {
     const TrainStep& s = a.steps[k];
+    const int h0 = s.in_dim, h1d = s.out_dim;
     const float* zin = zh + k * R * D;
-    const float* o = oh + k * R * 64;
-    // recompute yp (post ActNorm, post permutation) of this step
-    for (int i = tid; i < R * D; i += kF32Threads) {
+    const float* o0 = oh + (k * 2) * R * 64;
+    const float* o1 = o0 + R * 64;
+    for (int i = tid; i < R * D; i += kF32Threads) {             // recompute the coupling-order input of this step
       const int r = i / D, j = i - r * D;
-      const int pj = (int)s.perm[j];
-      tmp[i] = (zin[r * D + pj] + s.an_bias[pj]) * expf(s.an_logs[pj]);
+      const int pj = train_src_col(s, a.kind, j, hD0);
+      tmp[i] = glow ? (zin[r * D + pj] + s.an_bias[pj]) * expf(s.an_logs[pj]) : zin[r * D + pj];
     }
     __syncthreads();
-    // coupling transform backward -> d out of the network in act0 [R][Np3]; dzb[:, h0:] becomes d yp2
-    for (int i = tid; i < R * s.Np[2]; i += kF32Threads) act0[(i / s.Np[2]) * ld + (i % s.Np[2])] = 0.f;
-    __syncthreads();
-    for (int i = tid; i < R * h1d; i += kF32Threads) {
-      const int r = i / h1d, jj = i - r * h1d;
-      const long long gr = row0 + r;
-      const float g2 = dzb[r * D + h0 + jj];
-      if (a.coupling == GBNF_COUPLING_AFFINE) {
-        const float shift = o[r * 64 + 2 * jj], raw = o[r * 64 + 2 * jj + 1];
-        const float sg = 1.f / (1.f + expf(-(raw + 2.f)));
-        const float y2 = tmp[r * D + h0 + jj];
+    for (int net = a.nnets - 1; net >= 0; --net) {
+      // coupling transform backward -> d out of this network in act0 [R][Np3]; after the LAST network (net 0) dzb[:, h0:] = d z2
+      for (int i = tid; i < R * s.Np[2]; i += kF32Threads) act0[(i / s.Np[2]) * ld + (i % s.Np[2])] = 0.f;
+      __syncthreads();
+      for (int i = tid; i < R * h1d; i += kF32Threads) {
+        const int r = i / h1d, jj = i - r * h1d;
+        const long long gr = row0 + r;
+        const float g2 = dzb[r * D + h0 + jj];
         const float dldj = (gr < a.B) ? a.dldj[gr] : 0.f;
-        const float dsg = g2 * (y2 + shift) + dldj / sg;                  // out = (y2 + shift) sg ; ldj += log sg
-        act0[r * ld + 2 * jj] = g2 * sg;                                  // d shift
-        act0[r * ld + 2 * jj + 1] = dsg * sg * (1.f - sg);                // d raw
-        dzb[r * D + h0 + jj] = g2 * sg;                                   // d y2
-      } else {
-        act0[r * ld + jj] = g2;                                           // out = y2 + net ; d y2 = g2 unchanged
+        if (!glow) {
+          const float e = expf(o1[r * 64 + jj]);
+          if (net == 1) act0[r * ld + jj] = g2 * tmp[r * D + h0 + jj] * e + dldj;     // d scale: out = t + z2 e^s ; ldj += s
+          else { act0[r * ld + jj] = g2; dzb[r * D + h0 + jj] = g2 * e; }             // d shift ; d z2
+        } else if (a.coupling == GBNF_COUPLING_AFFINE) {
+          const float shift = o0[r * 64 + 2 * jj], raw = o0[r * 64 + 2 * jj + 1];
+          const float sg = 1.f / (1.f + expf(-(raw + 2.f)));
+          const float y2 = tmp[r * D + h0 + jj];
+          const float dsg = g2 * (y2 + shift) + dldj / sg;                  // out = (y2 + shift) sg ; ldj += log sg
+          act0[r * ld + 2 * jj] = g2 * sg;                                  // d shift
+          act0[r * ld + 2 * jj + 1] = dsg * sg * (1.f - sg);                // d raw
+          dzb[r * D + h0 + jj] = g2 * sg;                                   // d y2
+        } else {
+          act0[r * ld + jj] = g2;                                           // out = y2 + net ; d y2 = g2 unchanged
+        }
       }
+      __syncthreads();
+      for (int i = tid; i < R * s.Np[2]; i += kF32Threads) {
+        const int r = i / s.Np[2], j = i - r * s.Np[2];
+        const long long gr = row0 + r;
+        if (gr < a.B) s.d3[net][gr * s.Np[2] + j] = act0[r * ld + j];
+      }
+      const int ak = act_of(net);
+      // d h2 = d3 . W3   (nn.Linear layout: rows n, columns k)
+      gemm_layer_fp32<R, 0>(act0, act1, ld, s.Wn[net][2], a.zeros, s.NKp[2], s.KNp[2], Ws);
+      for (int i = tid; i < R * hp; i += kF32Threads) {
+        const int r = i / hp, j = i - r * hp;
+        const long long gr = row0 + r;
+        const float hv = (gr < a.B) ? s.h2[net][gr * hp + j] : 0.f;
+        const float d = act1[r * ld + j] * (ak == 2 ? act_grad_from_output<2>(hv) : act_grad_from_output<1>(hv));
+        act1[r * ld + j] = d;
+        if (gr < a.B) s.d2[net][gr * hp + j] = d;
+      }
+      __syncthreads();
+      gemm_layer_fp32<R, 0>(act1, act2, ld, s.Wn[net][1], a.zeros, s.NKp[1], s.KNp[1], Ws);
+      for (int i = tid; i < R * hp; i += kF32Threads) {
+        const int r = i / hp, j = i - r * hp;
+        const long long gr = row0 + r;
+        const float hv = (gr < a.B) ? s.h1[net][gr * hp + j] : 0.f;
+        const float d = act2[r * ld + j] * (ak == 2 ? act_grad_from_output<2>(hv) : act_grad_from_output<1>(hv));
+        act2[r * ld + j] = d;
+        if (gr < a.B) s.d1[net][gr * hp + j] = d;
+      }
+      __syncthreads();
+      gemm_layer_fp32<R, 0>(act2, act0, ld, s.Wn[net][0], a.zeros, s.NKp[0], s.KNp[0], Ws);      // d z1 [R][KNp0] (first h0 columns valid)
+      for (int i = tid; i < R * h0; i += kF32Threads) {
+        const int r = i / h0, j = i - r * h0;
+        dzb[r * D + j] += act0[r * ld + j];                                  // z1 passes through AND feeds the network(s)
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    for (int i = tid; i < R * s.Np[2]; i += kF32Threads) {
-      const int r = i / s.Np[2], j = i - r * s.Np[2];
-      const long long gr = row0 + r;
-      if (gr < a.B) s.d3[gr * s.Np[2] + j] = act0[r * ld + j];
-    }
-    // d h2 = d3 . W3   (nn.Linear layout: rows n, columns k)
-    gemm_layer_fp32<R, 0>(act0, act1, ld, s.Wn[2], a.zeros, s.NKp[2], s.KNp[2], Ws);
-    for (int i = tid; i < R * hp; i += kF32Threads) {
-      const int r = i / hp, j = i - r * hp;
-      const long long gr = row0 + r;
-      const float hv = (gr < a.B) ? s.h2[gr * hp + j] : 0.f;
-      const float d = act1[r * ld + j] * (a.act == GBNF_ACT_RELU ? act_grad_from_output<2>(hv) : act_grad_from_output<1>(hv));
-      act1[r * ld + j] = d;
-      if (gr < a.B) s.d2[gr * hp + j] = d;
-    }
-    __syncthreads();
-    gemm_layer_fp32<R, 0>(act1, act2, ld, s.Wn[1], a.zeros, s.NKp[1], s.KNp[1], Ws);
-    for (int i = tid; i < R * hp; i += kF32Threads) {
-      const int r = i / hp, j = i - r * hp;
-      const long long gr = row0 + r;
-      const float hv = (gr < a.B) ? s.h1[gr * hp + j] : 0.f;
-      const float d = act2[r * ld + j] * (a.act == GBNF_ACT_RELU ? act_grad_from_output<2>(hv) : act_grad_from_output<1>(hv));
-      act2[r * ld + j] = d;
-      if (gr < a.B) s.d1[gr * hp + j] = d;
-    }
-    __syncthreads();
-    gemm_layer_fp32<R, 0>(act2, act0, ld, s.Wn[0], a.zeros, s.NKp[0], s.KNp[0], Ws);      // d z1 [R][KNp0] (first h0 columns valid)
-    for (int i = tid; i < R * h0; i += kF32Threads) {
-      const int r = i / h0, j = i - r * h0;
-      dzb[r * D + j] += act0[r * ld + j];                                  // z1 passes through AND feeds the network
-    }
-    __syncthreads();
-    // permutation and ActNorm backward: dy[:, perm[j]] = dyp[:, j]; y = (x + b) e^logs
+    // back to the step's input order: d x[:, src[j]] = d tmp[:, j]; Glow: y = (x + b) e^logs
     //   dx = dy e^logs ; d logs[p] += sum_r dy y + sum_r dldj ; d bias[p] += sum_r dy e^logs
     for (int j = tid; j < D; j += kF32Threads) {
-      const int pj = (int)s.perm[j];
-      const float e = expf(s.an_logs[pj]);
+      const int pj = train_src_col(s, a.kind, j, hD0);
+      const float e = glow ? expf(s.an_logs[pj]) : 1.f;
       float gl = 0.f, gb = 0.f;
       for (int r = 0; r < R; ++r) {
         const float dy = dzb[r * D + j];
         gl += dy * tmp[r * D + j];
         gb += dy * e;
-        act1[r * ld + pj] = dy * e;                                        // d x in logical order (staged, then copied back)
+        act1[r * ld + pj] = dy * e;                                        // d x in input order (staged, then copied back)
       }
-      float dl = 0.f;
-      for (int r = 0; r < R; ++r) { const long long gr = row0 + r; if (gr < a.B) dl += a.dldj[gr]; }
-      atomicAdd(s.g_logs + pj, gl + dl);                                   // ldj += sum_j logs_j (layers.py:512-516)
-      atomicAdd(s.g_bias + pj, gb);
+      if (glow) {
+        float dl = 0.f;
+        for (int r = 0; r < R; ++r) { const long long gr = row0 + r; if (gr < a.B) dl += a.dldj[gr]; }
+        atomicAdd(s.g_logs + pj, gl + dl);                                 // ldj += sum_j logs_j (layers.py:512-516)
+        atomicAdd(s.g_bias + pj, gb);
+      }
     }
     __syncthreads();
     for (int i = tid; i < R * D; i += kF32Threads) { const int r = i / D, j = i - r * D; dzb[i] = act1[r * ld + j]; }

@@ -193,8 +193,10 @@ int gbnf_weight_renorm(gbnf_handle h, float* d_w, int64_t B, const double* d_wsu
  * dldj = -1 / B).  Recompute-in-kernel: the forward value comes from gbnf_component_logq and saves nothing; this call
  * recomputes the activations (fp32 CUDA-core arithmetic, reference-class numerics) and runs the backward sweep.
  * `p` holds the component's CURRENT raw parameters (as for gbnf_pack_component), `grads` the same tensors' gradient
- * buffers, which are OVERWRITTEN.  Glow components, coupling_network_depth 1, h <= 512, D <= 64; other configurations
- * return GBNF_ERR_INVALID and train through the caller's autograd.  d_dx_opt [B, D] (may be NULL) receives dL/dx. */
+ * buffers, which are OVERWRITTEN.  Glow components with a permutation (tanh / relu) and RealNVP components WITHOUT BatchNorm
+ * (tanh / relu / mixed; models/transformations.py:560-579 -- train-mode BatchNorm couples the rows of a batch), with
+ * coupling_network_depth 1, h <= 512, D <= 64; other configurations return GBNF_ERR_INVALID and train through the caller's
+ * autograd.  d_dx_opt [B, D] (may be NULL) receives dL/dx. */
 typedef struct {
   float* an_bias;
   float* an_logs;

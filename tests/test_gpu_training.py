@@ -22,15 +22,21 @@ CASES = {
     "glow_affine_relu_d21_h256": dict(kind="glow", D=21, C=2, K=4, h=256, act="relu"),
     "glow_affine_d64_h384": dict(kind="glow", D=64, C=2, K=2, h=384),
     "glow_affine_d2_h128": dict(kind="glow", D=2, C=2, K=2, h=128),
+    # RealNVP without BatchNorm: two networks per step, halves swapped on the flipped steps (odd D: |z1| alternates)
+    "realnvp_tanh_d6_h256": dict(kind="realnvp", D=6, C=3, K=5, h=256),
+    "realnvp_mixed_d5_h64": dict(kind="realnvp", D=5, C=2, K=4, h=64, act="mixed"),
+    "realnvp_relu_d2_h256": dict(kind="realnvp", D=2, C=2, K=1, h=256, act="relu"),
+    "realnvp_tanh_d43_h512": dict(kind="realnvp", D=43, C=2, K=3, h=512),
 }
 
 
 def _autograd_reference(model, c, x, dtype):
     """Gradients by torch autograd through forward_autograd (== the reference's forward) in `dtype`."""
     flow = copy.deepcopy(model.flows[c]).to(dtype)
-    for s_src, s_dst in zip(model.flows[c].steps(), flow.steps()):
-        s_dst.permutation.set_indices(s_src.permutation.indices)
-        s_dst.actnorm.inited = True
+    if model.component_type == "glow":
+        for s_src, s_dst in zip(model.flows[c].steps(), flow.steps()):
+            s_dst.permutation.set_indices(s_src.permutation.indices)
+            s_dst.actnorm.inited = True
     for p in flow.parameters():
         p.requires_grad_(True)
     z, ldj = flow.forward_autograd(x.to(dtype))
@@ -109,7 +115,8 @@ def test_training_step_through_the_driver_function_and_optimizer():
 
 
 def test_unsupported_configurations_fall_back_to_autograd():
-    md = orc.make_synthetic_model("realnvp", 6, 2, 2, 128, seed=3)
+    """RealNVP WITH BatchNorm: train-mode batch statistics couple the rows of a batch -> the caller's autograd."""
+    md = orc.make_synthetic_model("realnvp", 6, 2, 3, 128, seed=3, batch_norm=True)
     model = build_model(md, "cuda", gemm_mode="fp32")
     try:
         for p in model.flows[1].parameters():
