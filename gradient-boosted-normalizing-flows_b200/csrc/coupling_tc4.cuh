@@ -39,6 +39,7 @@ struct Tc4Misc {
   uint64_t l2f[2];    // MMA -> epilogue : layer-2 chunk in slot i accumulated                                (commit)
   uint64_t l3f;       // MMA -> epilogue : last layer of a pass accumulated                                   (commit)
   uint64_t l3d;       // epilogue -> MMA : the transform has read the last-layer accumulator ([448, 512) free)   (16 arrivals)
+  uint64_t c2r;       // epilogue -> MMA : layer-1 chunk 2's accumulator has been READ ([192, 256) may take half of chunk 3)  (16 arrivals)
   uint64_t w3full[2];
   uint64_t w3empty[2];
   uint32_t tmem_base;
@@ -107,6 +108,9 @@ __device__ __forceinline__ constexpr int t4_ccol(int j) { return 192 * (j >> 1) 
 constexpr uint32_t kT4Slot0 = 256u, kT4Slot1 = 384u, kT4LaCol = 448u;
 
 #define T4_CLK() (PROF ? clock64() : 0LL)
+// event trace of ONE slot (kT4TraceSlot) of CTA 0: a.prof[190 + id] = clock64() (tools/tc4_profile.py prints it)
+constexpr int kT4TraceSlot = 41;
+#define T4_TRACE(id) do { if (PROF && a.prof != nullptr && blockIdx.x == 0 && s == kT4TraceSlot && lane == 0) a.prof[190 + (id)] = clock64(); } while (0)
 // PROF = 1: per-role cycle counters of CTA 0 (gbnf_get_profile; tools/tc4_profile.py)
 template <int TANH_MODE, int PROF = 0>
 __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArgs a, TcPlan plan) {
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
       ptx::mbar_init(&misc->w3full[i], 1); ptx::mbar_init(&misc->w3empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) { ptx::mbar_init(&misc->a1r[i], 16); ptx::mbar_init(&misc->l1f[i], 1); }
-    ptx::mbar_init(&misc->l3f, 1); ptx::mbar_init(&misc->l3d, 16);
+    ptx::mbar_init(&misc->l3f, 1); ptx::mbar_init(&misc->l3d, 16); ptx::mbar_init(&misc->c2r, 16);
     ptx::fence_mbar_init();
     if (a.G_ll != nullptr) mixture_coefficients(a.rho, a.n_mix, a.skip_c, a.mix_mode, misc->coef);
   }
@@ -347,23 +351,37 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
         // (the upper half of chunk 2's accumulator, packed in place): the other chain's last-layer accumulator [448, 512) stays
         // untouched until its transform has read it.  Layer-2 chunk 0 starts behind layer-1 chunk 1 and still ends one
         // k-quarter after the last layer-1 epilogue.
+        T4_TRACE(0);
         l1_chunk(0);
+        T4_TRACE(1);
         if (s > 0) l3_piece(NJ - 1, false);
+        T4_TRACE(2);
         l1_chunk(1);
         wait_a1(0);
+        T4_TRACE(3);
         l1_chunk(2);
         wait_a1(1);
+        T4_TRACE(4);
         l2c0_part(0);
-        wait_a1(2);
+        tq = T4_CLK();
+        wait_epi(&misc->c2r, (uint32_t)ch, 28);   // chunk 2's accumulator has been read (well before its activation is done)
+        m_a1 += T4_CLK() - tq;
+        T4_TRACE(5);
         l1_chunk(3);                           // before the next parts: the in-order pipe would park it behind them
         l2c0_part(1);
+        wait_a1(2);
         l2c0_part(2);
+        T4_TRACE(6);
         wait_a1(3);
+        T4_TRACE(7);
         l2c0_part(3);
+        T4_TRACE(8);
         // ---- layer-2 chunks 1..4 with the last-layer pieces 0..3 ----
 #pragma unroll
         for (int j = 1; j < NJ; ++j) {
+          T4_TRACE(10 + 3 * (j - 1));            // chunk j: before the previous piece
           if (j >= 2) l3_piece(j - 2, j == 2 && s > 0);
+          T4_TRACE(11 + 3 * (j - 1));            // piece issued
           const int w = t4_cw(j);
           const int parts = (w == 128) ? 4 : 2;
 #pragma unroll
@@ -398,8 +416,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
             }
             __syncwarp();
           }
+          T4_TRACE(12 + 3 * (j - 1));            // chunk j issued
         }
+        T4_TRACE(22);
         l3_piece(NJ - 2, false);
+        T4_TRACE(23);
       }
     }
     if (npass > 0) l3_piece(NJ - 1, false);
@@ -505,6 +526,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
         uint32_t r[32];
         ptx::tmem_ld32(lane_base + col, r);
         ptx::tmem_ld_wait();
+        if (q == 2) {                         // chunk 3's second half may now be multiplied into [192, 256): its layer-1 GEMM then
+          ptx::tc_fence_before();             // runs under this chunk's activation instead of after it
+          t2_warp_arrive(&misc->c2r, lane);
+        }
         t2_act_pack32<1, TANH_MODE>(r, bias_c + g * 32 + q * kT2Chunk, pk, a.error_flag);
       }
       if (q >= 2) t2_quad_bar(quad);         // chunk 2 and half of chunk 3 accumulate inside the A1 region they are packed into
@@ -706,15 +731,20 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
 #pragma unroll 1
       for (int t = 0; t < 5; ++t) {
         const int j = (t == 0) ? NJ - 1 : t - 1;
+        if (warp_e == 0) T4_TRACE(40 + 8 * t);
         if (t == 0 ? (s > 0) : real) e2_chunk(j, t == 0 ? biasA : biasB);
+        if (warp_e == 0) T4_TRACE(41 + 8 * t);
         if (t == 0 && real) {
 #pragma unroll 1
-          for (int q = 0; q < NQ; ++q) e1_chunk(q, biasB, (uint32_t)ch);
+          for (int q = 0; q < NQ; ++q) { e1_chunk(q, biasB, (uint32_t)ch); if (warp_e == 0) T4_TRACE(44 + q); }
         }
-        // the finishing chain's transform goes where the epilogue would wait for layer-2 chunk 0 (its last k-quarter is still
-        // being multiplied); it also frees the last-layer accumulator before this pass's piece 0 needs it
-        if (t == 0 && s > 0) finish_a(fin, (uint32_t)(s - 1) & 1u);
-        if (t == 2) finish_b(fin, s <= 0);
+        // Placement (event trace, tools/tc4_profile.py): the slot's first half (A's last chunk, B's layer-1 phase, B's chunk 0) is
+        // epilogue bound, its second half (B's chunks 2 .. 4) tensor-pipe bound with ~3 k cycles of epilogue slack.  A's transform
+        // follows B's chunk 0 directly (its tensor-memory read releases [448, 512) just before B's piece 0 wants it); A's
+        // bookkeeping / x reload / gather / staging block (3 k) goes behind B's chunk 2, where it delays no packed piece.
+        if (t == 1 && s > 0) finish_a(fin, (uint32_t)(s - 1) & 1u);
+        if (t == 3) finish_b(fin, s <= 0);
+        if (warp_e == 0) T4_TRACE(42 + 8 * t);
       }
       tq = T4_CLK();
       ptx::cp_async_wait_all();
@@ -736,6 +766,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
 }
 
 #undef T4_CLK
+#undef T4_TRACE
 
 inline cudaError_t tc4_configure() {
   cudaError_t e = cudaFuncSetAttribute(coupling_tc4_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -49,3 +49,19 @@ print("per-CTA MMA-warp total cycles: min %d  median %d  max %d ; all waits: min
 print("slowest CTAs:", sorted(range(ng), key=lambda i: -tot[i])[:12])
 print("totals by CTA (k cycles):", [t // 1000 for t in tot])
 print("busy (total - waits) by CTA (k cycles):", [(t - r) // 1000 for t, r in zip(tot, ring)])
+
+names = {0: "MMA slot start (ring stage + a0r ok)", 1: "MMA L1(0) issued", 2: "MMA prev L3(4) issued", 3: "MMA a1r[0] seen", 4: "MMA a1r[1] seen",
+         5: "MMA a1r[2] seen", 6: "MMA L2c0 parts 1,2 issued", 7: "MMA a1r[3] seen", 8: "MMA L2c0 part 3 issued",
+         10: "MMA c1: start", 11: "MMA c1: (no piece)", 12: "MMA c1 issued", 13: "MMA c2: start", 14: "MMA L3(0) issued", 15: "MMA c2 issued",
+         16: "MMA c3: start", 17: "MMA L3(1) issued", 18: "MMA c3 issued", 19: "MMA c4: start", 20: "MMA L3(2) issued", 21: "MMA c4 issued",
+         22: "MMA before L3(3)", 23: "MMA L3(3) issued",
+         40: "EPI t0 start", 41: "EPI E2[4](A) done", 44: "EPI E1[0] done", 45: "EPI E1[1] done", 46: "EPI E1[2] done", 47: "EPI E1[3] done",
+         42: "EPI transform(A) done", 48: "EPI t1 start", 49: "EPI E2[0] done", 50: "EPI t1 end", 56: "EPI t2 start", 57: "EPI E2[1] done",
+         58: "EPI finish_b(A) done", 64: "EPI t3 start", 65: "EPI E2[2] done", 66: "EPI t3 end", 72: "EPI t4 start", 73: "EPI E2[3] done", 74: "EPI t4 end"}
+full = model.trace()
+ev = [(full[158 + i], names[i]) for i in names if full[158 + i] > 0]   # a.prof[190 + id] = trace[158 + id]
+if ev:
+    t0 = min(t for t, _ in ev)
+    print("event trace of slot 41 of CTA 0 (cycles from the first event):")
+    for t, n in sorted(ev):
+        print(f"  {t - t0:7d}  {n}")
