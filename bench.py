@@ -489,7 +489,8 @@ def run_ours(a):
         src = tj.get("_source")
         traffic_src = src.get(f"{a.config}:{a.mode}:{a.batch}") if isinstance(src, dict) else src
     inf = model.info()
-    kname = ("coupling_fp32_kernel" if a.mode == "fp32" else "coupling_tc4_kernel (two-chain, tcgen05)" if inf.get("two_chain") else
+    kname = ("coupling_fp32_kernel" if a.mode == "fp32" else "coupling_tc5_kernel (interleaved s / t networks, tcgen05)" if inf.get("two_chain") == 2 else
+             "coupling_tc4_kernel (two-chain, tcgen05)" if inf.get("two_chain") == 1 else
              "coupling_tc3_kernel (CTA pair, tcgen05)" if inf["pipelined"] == 2 else "coupling_tc2_kernel (pipelined, tcgen05)" if inf["pipelined"] == 1
              else "coupling_tc_kernel (serial, tcgen05)")
     out = {

@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nst = plan.nst;
   // uniform step geometry (tc4_eligible)
-  const int in_dim = __ldg(&a.steps[0].in_dim), out_dim = __ldg(&a.steps[0].out_dim);
-  const int k0p = __ldg(&a.steps[0].layer[0][0].Kp), np3 = __ldg(&a.steps[0].layer[0][2].Np);
+  const int in_dim = __ldg(&a.steps[a.c0 * md.K].in_dim), out_dim = __ldg(&a.steps[a.c0 * md.K].out_dim);
+  const int k0p = __ldg(&a.steps[a.c0 * md.K].layer[0][0].Kp), np3 = __ldg(&a.steps[a.c0 * md.K].layer[0][2].Np);
   const int k0s = k0p >> 4;
   const uint32_t w3_stride = (uint32_t)np3 * 256u;     // bytes per last-layer piece buffer
   // passes per chain of this CTA

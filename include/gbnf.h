@@ -265,7 +265,8 @@ typedef struct {
   int32_t pipelined;       /* 2: CTA-pair tensor-core kernel for h = 1024 (coupling_tc3.cuh), 1: chunk-pipelined tensor-core
                               kernel (coupling_tc2.cuh), 0: serial tensor-core / fp32 kernel */
   int32_t two_chain;       /* 1: the last coupling launch ran the two-chain schedule (coupling_tc4.cuh: Glow / affine / tanh, h = 512,
-                              an even number of components per work unit) */
+                              an even number of components per work unit); 2: the interleaved s / t schedule (coupling_tc5.cuh:
+                              RealNVP / tanh, h = 256) */
 } gbnf_info;
 int gbnf_get_info(gbnf_handle h, gbnf_info* out);
 

@@ -97,3 +97,65 @@ def test_reference_golden_h512():
     assert inf["two_chain"] == 1
     ref = g["logq64"]
     assert np.max(np.abs(lq.cpu().numpy() - ref) / np.abs(ref)) < 1e-4
+
+
+# ---- interleaved s / t kernel for RealNVP, h = 256 (csrc/coupling_tc5.cuh) ------------------------------------------------------
+def _run5(md, x, mode, tc5, n_mix=None):
+    old = os.environ.get("GBNF_TC5")
+    try:
+        if tc5 is None:
+            os.environ.pop("GBNF_TC5", None)
+        else:
+            os.environ["GBNF_TC5"] = str(tc5)
+        m = build_model(md, "cuda", gemm_mode=mode)
+        m.pack_all()
+    finally:
+        if old is None:
+            os.environ.pop("GBNF_TC5", None)
+        else:
+            os.environ["GBNF_TC5"] = old
+    try:
+        G, lq = m.mixture_log_density(x, md["C"] if n_mix is None else n_mix, return_logq=True)
+        z, ldj = m.component_forward(x, md["C"] - 1)
+        m.check_status()
+        torch.cuda.synchronize()
+        return G.clone(), lq.clone(), z.clone(), ldj.clone(), m.info()
+    finally:
+        m.release()
+
+
+@pytest.mark.parametrize("mode", ["f16fast", "f16"])
+@pytest.mark.parametrize("D,C,K,B,bn,toy", [(6, 4, 5, 65536 + 33, False, False), (2, 8, 2, 5000, False, True), (5, 3, 4, 777, True, False),
+                                           (21, 2, 3, 300, True, False), (32, 2, 2, 129, False, False)])
+def test_realnvp_interleaved_matches_serial_networks(D, C, K, B, bn, toy, mode):
+    """Same operands as the serial-network kernel; only the last layer's two k-pieces are summed in registers instead of in the
+    tensor-core accumulator -> equal to fp32 rounding.  Odd D (the halves alternate), eval-BatchNorm, the toy base, z_out."""
+    md = orc.make_synthetic_model("realnvp", D, C, K, 256, seed=20 + D, batch_norm=bn, toy_base=toy)
+    x = torch.from_numpy(np.random.default_rng(D).standard_normal((B, D)).astype(np.float32)).cuda()
+    G2, lq2, z2, l2, inf2 = _run5(md, x, mode, None)
+    G1, lq1, z1, l1, inf1 = _run5(md, x, mode, 0)
+    assert inf2["two_chain"] == 2 and inf1["two_chain"] == 0 and inf2["pipelined"] == 1
+    for a_, b_ in ((lq2, lq1), (G2, G1), (z2, z1), (l2, l1)):
+        d = (a_ - b_).abs().double()
+        # fp32 summation order of the last layer only: 1e-7-level differences on average; on a handful of the 400 k values that
+        # last bit flips the fp16 rounding of a later step's activation (2^-11 relative), i.e. the difference between two equally
+        # valid fp16 roundings (f16 tolerance class, measured max 3.4e-4)
+        rel = d / (b_.abs().double() + 1.0)
+        assert float(rel.mean()) < 2e-6 and float(rel.max()) < 2e-3, (float(rel.mean()), float(rel.max()))
+    n = min(B, 2048)
+    ref = orc.all_component_logq(orc.cast_model(md, np.float64), x[:n].cpu().numpy().astype(np.float64))
+    np.testing.assert_allclose(lq2[:n].cpu().numpy(), ref, rtol=1e-4, atol=2e-2)
+
+
+def test_realnvp_interleaved_partial_mixture_and_rows_independent():
+    md = orc.make_synthetic_model("realnvp", 6, 4, 5, 256, seed=4)
+    x = torch.from_numpy(np.random.default_rng(2).standard_normal((4096 + 5, 6)).astype(np.float32)).cuda()
+    m = build_model(md, "cuda", gemm_mode="f16fast")
+    try:
+        G = m.mixture_log_density(x, 3)
+        assert m.info()["two_chain"] == 2
+        for a_, b_ in ((0, 1), (7, 140), (1000, 4101)):
+            assert torch.equal(m.mixture_log_density(x[a_:b_].contiguous(), 3), G[a_:b_])
+        m.check_status()
+    finally:
+        m.release()
