@@ -139,6 +139,8 @@ const char* watchdog_text(int code) {
     case 22: return "MMA issuer waiting for an A1 quarter";
     case 23: return "MMA issuer waiting for a packed A2 piece";
     case 24: return "MMA issuer waiting for last-layer weights";
+    case 25: return "MMA issuer waiting for a shipped-half slot to be read";
+    case 26: return "MMA issuer waiting for a last-layer piece product to be read";
     case 27: return "MMA issuer waiting for the last-layer accumulator to be read";
     case 28: return "MMA issuer waiting for layer-1 chunk 2 to be read";
     case 30: return "epilogue waiting for a layer-1 accumulator";
