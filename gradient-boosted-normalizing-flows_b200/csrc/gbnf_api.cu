@@ -18,6 +18,7 @@
 #include "coupling_tc3.cuh"
 #include "coupling_tc4.cuh"
 #include "coupling_tc5.cuh"
+#include "coupling_tc6.cuh"
 #include "train_bwd.cuh"
 
 using namespace gbnf;
@@ -100,6 +101,8 @@ struct gbnf_ctx {
   bool tc4_force = false;        // GBNF_TC4=2
   bool tc5 = false;              // interleaved s / t kernel (coupling_tc5.cuh) available: RealNVP / tanh, h = 256
   TcPlan tc5plan{};
+  bool tc6 = false;              // two-chain kernel for RealNVP / tanh, h = 256 (coupling_tc6.cuh)
+  TcPlan tc6plan{};
   int tc3_pairs = 0;             // CTA pairs the device keeps resident at once (cudaOccupancyMaxActiveClusters)
   int profiling = 0;             // GBNF_PROF=1: cycle counters + event trace, 2: event trace only (gbnf_get_profile / _trace)
   int last_grid = 0;
@@ -278,12 +281,18 @@ int plan_layout(gbnf_ctx* h) {
       h->tc4_force = h->tc4 && no_tc4 && no_tc4[0] == '2';
       const char* no_tc5 = std::getenv("GBNF_TC5");    // GBNF_TC5=0 keeps the serial-network kernel (A/B measurements)
       h->tc5 = tc5_eligible(md, h->steps_h) && !(no_tc5 && no_tc5[0] == '0') && tc5_make_plan(md, h->steps_h, &h->tc5plan);
+      // two component chains for RealNVP: OPT-IN (GBNF_TC6=1, or 2 = also prefer even work units): measured 13 % SLOWER than the
+      // interleaved s / t kernel on cfg2, kept for the A/B and as a tested building block
+      const char* use_tc6 = std::getenv("GBNF_TC6");
+      h->tc6 = use_tc6 && (use_tc6[0] == '1' || use_tc6[0] == '2') && tc6_eligible(md, h->steps_h) && tc6_make_plan(md, h->steps_h, &h->tc6plan);
+      if (h->tc6 && use_tc6[0] == '2') h->tc4_force = true;
     } else if (!tc_make_plan(md, h->steps_h, &h->tc, &why)) {
       return fail(GBNF_ERR_INVALID, "f16 tensor-core path: " + why);
     }
     h->tc.tanh_mode = (c.gemm_mode == GBNF_GEMM_F16_TC_FAST) ? 0 : 1;
     h->tc4plan.tanh_mode = h->tc.tanh_mode;
     h->tc5plan.tanh_mode = h->tc.tanh_mode;
+    h->tc6plan.tanh_mode = h->tc.tanh_mode;
     { const char* pe = std::getenv("GBNF_PROF"); h->profiling = (pe && pe[0] >= '1' && pe[0] <= '2') ? pe[0] - '0' : 0; }
     h->rows_per_cta = 128;
     h->smem_bytes = h->tc.smem_bytes;
@@ -353,7 +362,7 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
     // The two-chain kernel pairs the two halves of a unit's components: every unit needs the same, even number of them.  A pass
     // of it takes ~0.8 of a single-chain pass, which the cost model weighs against the coarser units (GBNF_TC4=2: always
     // prefer it when a split allows it -- tests).
-    const bool tc4_ok = h->tc4 && h->profiling != 2 && z_out == nullptr;
+    const bool tc4_ok = ((h->tc4 && h->profiling != 2) || (h->tc6 && h->profiling == 0)) && z_out == nullptr;
     bool best_two = false;
     for (int S = 1; S <= ncomp; S *= 2) {
       const int cpu = (ncomp + S - 1) / S;
@@ -392,11 +401,12 @@ int launch_coupling(gbnf_ctx* h, const float* x, long long B, int c0, int c1, fl
     else if (R == 32) coupling_fp32_kernel<32><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
     else coupling_fp32_kernel<16><<<grid, kF32Threads, h->smem_bytes, st>>>(a, h->ld, h->out_max);
   } else {
-    const bool st_interleaved = h->tc5 && h->profiling == 0;
-    int rc = st_interleaved ? tc5_launch(a, h->tc5plan, grid, st)
+    const bool st_interleaved = h->tc5 && h->profiling == 0 && !two_chain;
+    int rc = (two_chain && h->tc6) ? tc6_launch(a, h->tc6plan, grid, st)
+           : st_interleaved ? tc5_launch(a, h->tc5plan, grid, st)
            : two_chain ? tc4_launch(a, h->tc4plan, grid, st, h->profiling)
            : h->tc3 ? tc3_launch(a, h->tc, grid, st, h->profiling) : h->tc2 ? tc2_launch(a, h->tc, grid, st, h->profiling) : tc_launch(a, h->tc, grid, st);
-    h->last_two_chain = two_chain ? 1 : st_interleaved ? 2 : 0;
+    h->last_two_chain = (two_chain && h->tc6) ? 3 : two_chain ? 1 : st_interleaved ? 2 : 0;
     if (rc != 0) return fail(GBNF_ERR_INVALID, "f16 tensor-core path: launch configuration rejected");
   }
   h->launches++;
@@ -492,6 +502,7 @@ int gbnf_create(gbnf_handle* out, const gbnf_config* cfg) {
     CREATE_TRY(tc3_configure());
     CREATE_TRY(tc4_configure());
     CREATE_TRY(tc5_configure());
+    CREATE_TRY(tc6_configure());
     if (h->tc3) h->tc3_pairs = tc3_max_pairs(h->tc, h->num_sms);
   }
 #undef CREATE_TRY
