@@ -47,9 +47,7 @@ inline bool tc5_eligible(const ModelDims& md, const std::vector<StepDesc>& steps
   for (const StepDesc& s : steps)
     for (int n = 0; n < 2; ++n)
       if (s.layer[n][0].Kp != s0.layer[0][0].Kp || s.layer[n][2].Np != s0.layer[0][2].Np) return false;
-  // K = 1 (one step per component, BASELINE configuration 1) measured 2 % slower than the serial-network kernel: the per-component
-  // start / end dominates there and this kernel's x reload is the simple one
-  return md.K >= 2 && s0.layer[0][0].Kp <= 32 && s0.layer[0][2].Np <= 64;
+  return s0.layer[0][0].Kp <= 32 && s0.layer[0][2].Np <= 64;
 }
 
 __host__ __device__ inline uint32_t t5_bias_floats(int np3) { return 2u * (512u + (uint32_t)np3); }   // b1 b2 b3 of t, then of s
@@ -64,7 +62,7 @@ inline bool tc5_make_plan(const ModelDims& md, const std::vector<StepDesc>& step
   p->off_zs = o;   o = al(o + kTcRows * md.Dv * 4);
   p->off_a0 = o;   o = al(o + (k0p / 16) * 4096);
   p->off_a1 = o;   o = al(o + 6 * kTcRows * 4);                   // per-row partial sums at a component's end
-  p->off_sh = o;
+  p->off_sh = o;   o = al(o + kTcRows * md.D * 4);                 // the untransformed x tile of the unit (every component restarts from it)
   p->off_misc = o; o = al(o + kT2MiscBytes);
   p->off_bias = o; o = al(o + 2 * t5_bias_floats(np3) * 4);       // this pass | next pass
   p->off_tab = o;  o = al(o + 2 * 2 * kEpPad * 16);               // z1 | z2 tables of this step and of the next
@@ -89,6 +87,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc5_kernel(CouplingArg
   float* const zs = reinterpret_cast<float*>(smem + plan.off_zs);
   unsigned char* const A0 = smem + plan.off_a0;
   float* const part_s = reinterpret_cast<float*>(smem + plan.off_a1);
+  float* const xs = reinterpret_cast<float*>(smem + plan.off_sh);
   float* const bias_s = reinterpret_cast<float*>(smem + plan.off_bias);
   float4* const tab_s = reinterpret_cast<float4*>(smem + plan.off_tab);
   Tc5Misc* const misc = reinterpret_cast<Tc5Misc*>(smem + plan.off_misc);
@@ -297,15 +296,29 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc5_kernel(CouplingArg
         const CompDesc* cdp = a.comps + c;
         const float2 cconst = __ldg(reinterpret_cast<const float2*>(a.fblob + a.cc_off) + c);
         const long long base_off = (md.base == GBNF_BASE_STD_NORMAL) ? 0LL : __ldg(&cdp->base_off);
-        // ---- x rows -> z tile (every thread loads the columns it owns; L2 hits after the unit's first component) ----
-        {
-          float v[16];
+        // ---- x tile: fetched from HBM once per unit (coalesced, 8 loads in flight per thread) and kept in shared memory; every
+        //      component restarts from it (with K = 1 a component is one step: a global reload per component cost 2 %) ----
+        if (c == cb) {
+          const int total = kTcRows * D;
+          const long long gbase = (long long)tile * kTcRows * D;
+          const long long glimit = a.B * (long long)D;
+          for (int i0 = et; i0 < total; i0 += 8 * kT2EpiThreads) {
+            float v[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = (h0col + i < h1col && gr < a.B) ? __ldg(a.x + gr * D + h0col + i) : 0.f;
+            for (int uu = 0; uu < 8; ++uu) {
+              const int i = i0 + uu * kT2EpiThreads;
+              v[uu] = (i < total && gbase + i < glimit) ? __ldg(a.x + gbase + i) : 0.f;
+            }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) if (h0col + i < h1col) zrow[h0col + i] = v[i];
-          if (g == 0) for (int pc = D; pc < Dv; ++pc) zrow[pc] = 0.f;
+            for (int uu = 0; uu < 8; ++uu) {
+              const int i = i0 + uu * kT2EpiThreads;
+              if (i < total) xs[i] = v[uu];
+            }
+          }
+          t2_epi_bar();
         }
+        for (int pc = h0col; pc < h1col; ++pc) zrow[pc] = xs[row * D + pc];
+        if (g == 0) for (int pc = D; pc < Dv; ++pc) zrow[pc] = 0.f;
         ptx::cp_async_wait_all();
         t2_epi_bar();
         float lsum = 0.f;

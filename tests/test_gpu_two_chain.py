@@ -143,7 +143,7 @@ def test_realnvp_interleaved_and_two_chain_kernels(D, C, K, B, bn, toy, mode):
     G6, lq6, z6, l6, inf6 = _run_rnvp(md, x, mode, None, 2)
     G5, lq5, z5, l5, inf5 = _run_rnvp(md, x, mode, None, None)     # the default
     G2, lq2, z2, l2, inf2 = _run_rnvp(md, x, mode, 0, None)
-    assert inf6["two_chain"] == 3 and inf5["two_chain"] == (2 if K >= 2 else 0) and inf2["two_chain"] == 0
+    assert inf6["two_chain"] == 3 and inf5["two_chain"] == 2 and inf2["two_chain"] == 0
     if K >= 2:
         assert torch.equal(lq6, lq5) and torch.equal(G6, G5)
     for a_, b_ in ((lq6, lq2), (G6, G2), (z6, z2), (l6, l2)):
