@@ -165,8 +165,9 @@ int gbnf_mixture_logdensity(gbnf_handle h, const float* d_logq, int64_t B, int32
                             const float* d_rho, int32_t skip_c, int32_t mix_mode, float* d_G_ll, void* stream);
 
 /* Single-pass fused path: components [0, n_comp) + mixture; the [B, C] matrix never goes to HBM unless
- * d_logq_opt (ld = n_comp) is given.  Also leaves the batch softmax statistics of -G_ll (max, sum exp) in the
- * handle so that a following gbnf_boost_weights on the same d_G_ll needs no extra reduction pass. */
+ * d_logq_opt (ld = n_comp) is given.  (The batch softmax statistics of -G_ll are NOT a by-product of this call:
+ * gbnf_boost_weights makes its own one-sweep reduction over G_ll, 4 bytes per row -- 0.4 % of the fused step at the
+ * headline configuration, profiles/r02c_launches_cfg3_steps.csv.) */
 int gbnf_fused_eval(gbnf_handle h, const float* d_x, int64_t B, int32_t n_comp, const float* d_rho,
                     int32_t skip_c, int32_t mix_mode, float* d_G_ll, float* d_logq_opt, void* stream);
 
