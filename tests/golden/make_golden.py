@@ -96,7 +96,8 @@ def ref_forward_all(model, x, toy_base):
     return torch.stack(zs, 0), torch.stack(ldjs, 0), torch.stack(lqs, 1)
 
 
-def build_case(name):
+def build_case(name, out_dir=None):
+    """out_dir: where to write (default: next to this script); tests/test_golden_regeneration.py regenerates into a temp dir."""
     kw, seed, B, toy_base = CONFIGS[name]
     kw = dict(kw)
     args = make_args(kw.pop("kind"), kw.pop("D"), kw.pop("C"), kw.pop("K"), kw.pop("h"), **kw)
@@ -306,7 +307,7 @@ def build_case(name):
         out["grid.total_prob"] = total.numpy()
         for c in range(C):
             out[f"grid.prob.c{c}"] = axs[(int(1 + np.floor(c / plt_width)), int(c % plt_width))].grids[0].numpy()
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(out_dir or HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), |logq32-logq64|max = "
           f"{np.abs(lq32.numpy() - lq64.numpy()).max():.3e}")
