@@ -90,6 +90,9 @@ struct CouplingArgs {
   float* logq_peers[kMaxRanks];
   int n_peers, peer_ld, peer_col0;
   int exp_flags;                   // experiments (GBNF_EXP env, diagnostics only): bit 0 = producer skips the weight copies
+  int terms_only;                  // 1: write the mixture terms of [c0, c1) but leave the tile's logsumexp to a LATER launch of the
+                                   // remaining components (an odd number of components: two-chain kernel on the even part, then
+                                   // the single-chain kernel on the last component, which reduces all n_mix terms)
   int* error_flag;                 // status words in MAPPED HOST memory (the host can read them after a trap, without a
                                    // synchronisation): [0] watchdog code of a timed-out wait, [1] fp16 weight overflow (pack),
                                    // [2] a value entering an fp16 GEMM operand was not finite in fp16

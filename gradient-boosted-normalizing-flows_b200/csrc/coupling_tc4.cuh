@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) coupling_tc4_kernel(CouplingArg
         }
         if (a.G_ll != nullptr && c < a.n_mix) __stcg(a.lse_terms + ((long long)tile * kTcRows + row) * a.n_mix + c, misc->coef[c] + lq);
       }
-      if (chain == 1 && c + 1 == p.cend && a.G_ll != nullptr) {
+      if (chain == 1 && c + 1 == p.cend && a.G_ll != nullptr && !a.terms_only) {
         bool last = true;
         if (a.split > 1) {
           if (g == 0) __threadfence();

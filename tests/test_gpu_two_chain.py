@@ -179,3 +179,23 @@ def test_realnvp_two_chain_partial_mixture_and_rows_independent():
         m.check_status()
     finally:
         m.release()
+
+
+def test_odd_component_counts_use_two_chain_for_the_even_part():
+    """n = 3, 5, 7 components: two-chain kernel on the first n - 1 (mixture terms only), single-chain kernel on the last one, whose
+    reduce covers all terms -> bitwise equal to the single-chain kernel on all n; also the log q matrix and a large ragged batch."""
+    md = orc.make_synthetic_model("glow", 43, 8, 3, 512, seed=6)
+    x = torch.from_numpy(np.random.default_rng(11).standard_normal((20000 + 3, 43)).astype(np.float32)).cuda()
+    m = _model(md, "f16fast", None)
+    m0 = _model(md, "f16fast", 0)
+    try:
+        for n_mix in (3, 5, 7):
+            l0 = m.info()["launches"]
+            G, lq = m.mixture_log_density(x, n_mix, return_logq=True)
+            assert m.info()["launches"] - l0 == 2, "even part + last component"
+            G0, lq0 = m0.mixture_log_density(x, n_mix, return_logq=True)
+            assert torch.equal(G, G0) and torch.equal(lq, lq0)
+        assert torch.equal(m.component_log_density(x, 1, 6), m0.component_log_density(x, 1, 6))      # 5 components, log q only
+        m.check_status()
+    finally:
+        m.release(); m0.release()
