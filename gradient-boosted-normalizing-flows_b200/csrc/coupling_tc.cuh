@@ -105,6 +105,40 @@ __device__ __forceinline__ float fmax_nan(float a, float b) {
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
+__device__ __forceinline__ float fmin_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+// Four activations of one row at once.  The accurate tanh costs two MUFU operations per value (ex2 + rcp), and the MUFU pipe
+// (16 / clk / SM) is what bounds the accurate mode: one reciprocal serves four values (1 / (a0 a1 a2 a3), then the partial
+// products give each 1 / a_i back) -> 1.25 MUFU + 2.5 FMA-pipe operations per value instead of 2 + 1.  a_i = e^(2 v_i) + 1 with
+// 2 v_i capped at 20 (tanh(10) rounds to 1 in fp32), so the product of four stays below 5.5e34; NaN passes the cap (min.NaN)
+// and poisons only values of the same row; v = -inf gives a = 1 -> -1.  Error: 3 ulp on 1 / a_i -> < 4e-7 absolute on tanh.
+template <int ACT, int TANH_MODE>
+__device__ __forceinline__ void tc_act4(float& v0, float& v1, float& v2, float& v3) {
+  if (ACT == 1 && TANH_MODE != 0) {
+    const float c = 2.8853900817779268f, cap = 28.853900817779268f;
+    float e0, e1, e2, e3, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmin_nan(v0 * c, cap)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmin_nan(v1 * c, cap)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmin_nan(v2 * c, cap)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmin_nan(v3 * c, cap)));
+    const float a0 = e0 + 1.0f, a1 = e1 + 1.0f, a2 = e2 + 1.0f, a3 = e3 + 1.0f;
+    const float p01 = a0 * a1, p23 = a2 * a3;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+    const float rm = -2.0f * r, r01 = rm * p23, r23 = rm * p01;          // -2 / (a0 a1), -2 / (a2 a3)
+    v0 = fmaf(r01, a1, 1.0f);
+    v1 = fmaf(r01, a0, 1.0f);
+    v2 = fmaf(r23, a3, 1.0f);
+    v3 = fmaf(r23, a2, 1.0f);
+  } else {
+    v0 = tc_act<ACT, TANH_MODE>(v0);
+    v1 = tc_act<ACT, TANH_MODE>(v1);
+    v2 = tc_act<ACT, TANH_MODE>(v2);
+    v3 = tc_act<ACT, TANH_MODE>(v3);
+  }
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -133,14 +167,12 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tbase, int quad, int
     for (int q = 0; q < 4; ++q) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * q));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * q + 4));
-      const float v0 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 0]) + b0.x);
-      const float v1 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 1]) + b0.y);
-      const float v2 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 2]) + b0.z);
-      const float v3 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 3]) + b0.w);
-      const float v4 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 4]) + b1.x);
-      const float v5 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 5]) + b1.y);
-      const float v6 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 6]) + b1.z);
-      const float v7 = tc_act<ACT, TANH_MODE>(__uint_as_float(r[8 * q + 7]) + b1.w);
+      float v0 = __uint_as_float(r[8 * q + 0]) + b0.x, v1 = __uint_as_float(r[8 * q + 1]) + b0.y;
+      float v2 = __uint_as_float(r[8 * q + 2]) + b0.z, v3 = __uint_as_float(r[8 * q + 3]) + b0.w;
+      float v4 = __uint_as_float(r[8 * q + 4]) + b1.x, v5 = __uint_as_float(r[8 * q + 5]) + b1.y;
+      float v6 = __uint_as_float(r[8 * q + 6]) + b1.z, v7 = __uint_as_float(r[8 * q + 7]) + b1.w;
+      tc_act4<ACT, TANH_MODE>(v0, v1, v2, v3);
+      tc_act4<ACT, TANH_MODE>(v4, v5, v6, v7);
       if (ACT == 2 && !(fmax_nan(fmax_nan(fmax_nan(v0, v1), fmax_nan(v2, v3)), fmax_nan(fmax_nan(v4, v5), fmax_nan(v6, v7))) <= 65504.f))
         *reinterpret_cast<volatile int*>(status + 2) = 1;                           // ReLU activation not finite in fp16
       st_shared_v4(A1 + a_chunk_off(row, c0 + 8 * q), pack_half2(v0, v1), pack_half2(v2, v3), pack_half2(v4, v5),

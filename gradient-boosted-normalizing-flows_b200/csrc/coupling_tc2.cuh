@@ -124,10 +124,11 @@ __device__ __forceinline__ void t2_act_pack16(const uint32_t (&r)[16], const flo
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);      // staged in shared memory (broadcast read)
-    p[2 * q + 0] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 0]) + b.x),
-                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 1]) + b.y));
-    p[2 * q + 1] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 2]) + b.z),
-                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 3]) + b.w));
+    float v0 = __uint_as_float(r[4 * q + 0]) + b.x, v1 = __uint_as_float(r[4 * q + 1]) + b.y;
+    float v2 = __uint_as_float(r[4 * q + 2]) + b.z, v3 = __uint_as_float(r[4 * q + 3]) + b.w;
+    tc_act4<ACT, TANH_MODE>(v0, v1, v2, v3);
+    p[2 * q + 0] = pack_half2(v0, v1);
+    p[2 * q + 1] = pack_half2(v2, v3);
   }
 }
 // 32 accumulator values of one row -> bias + activation -> 16 packed fp16 pairs
@@ -142,10 +143,11 @@ __device__ __forceinline__ void t2_act_pack32(const uint32_t (&r)[32], const flo
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
-    p[2 * q + 0] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 0]) + b.x),
-                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 1]) + b.y));
-    p[2 * q + 1] = pack_half2(tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 2]) + b.z),
-                              tc_act<ACT, TANH_MODE>(__uint_as_float(r[4 * q + 3]) + b.w));
+    float v0 = __uint_as_float(r[4 * q + 0]) + b.x, v1 = __uint_as_float(r[4 * q + 1]) + b.y;
+    float v2 = __uint_as_float(r[4 * q + 2]) + b.z, v3 = __uint_as_float(r[4 * q + 3]) + b.w;
+    tc_act4<ACT, TANH_MODE>(v0, v1, v2, v3);
+    p[2 * q + 0] = pack_half2(v0, v1);
+    p[2 * q + 1] = pack_half2(v2, v3);
   }
 }
 

@@ -142,7 +142,11 @@ __device__ __forceinline__ void t3_act_pack32_add(const uint32_t (&r)[32], const
     if (!(mx <= 65504.f)) *reinterpret_cast<volatile int*>(status + 2) = 1;
   }
 #pragma unroll
-  for (int q = 0; q < 16; ++q) p[q] = pack_half2(tc_act<ACT, TANH_MODE>(v[2 * q]), tc_act<ACT, TANH_MODE>(v[2 * q + 1]));
+  for (int q = 0; q < 8; ++q) {
+    tc_act4<ACT, TANH_MODE>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    p[2 * q] = pack_half2(v[4 * q], v[4 * q + 1]);
+    p[2 * q + 1] = pack_half2(v[4 * q + 2], v[4 * q + 3]);
+  }
 }
 
 // PROF = 1: per-role cycle counters of CTA 0 (rank 0 of pair 0) in a.prof (gbnf_get_profile): [0] MMA warp total, [1] wait ring,
